@@ -1,0 +1,254 @@
+"""ctypes binding of include/dartgpu.h — the host-side mirror of the reference's per-read interface.
+
+The names follow the reference functions each call replaces (src/structure.h:192-233):
+
+    Mapper.identify_seed_pairs(reads)      IdentifySeedPairs + GenerateAlignmentCandidate, batched
+    Mapper.kmer_reseed(bases, jobs)        GenerateLongestSimplePairsFromFragmentPair, batched
+    Mapper.nw_alignment(bases, jobs)       nw_alignment, batched
+    Mapper.map_reads(reads)                the body of ReadMapping()'s per-read loop
+
+There is no CPU path here: if libdartgpu.so is missing or no CUDA device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdartgpu.so")
+
+
+class DartGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dartgpu error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("max_gaps", C.c_int32), ("max_intron", C.c_int32), ("min_intron", C.c_int32),
+                ("max_mismatch", C.c_int32), ("max_dup", C.c_uint32), ("multi_hit", C.c_int32),
+                ("pair_end", C.c_int32), ("all_sj", C.c_int32), ("unique", C.c_int32), ("host_threads", C.c_int32)]
+
+
+class _Reads(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("bases", C.c_void_p), ("offsets", C.c_void_p)]
+
+
+class _Seeds(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("seed_off", "seed_gpos", "seed_rpos", "seed_len",
+                                           "cand_off", "cand_begin", "cand_count", "cand_score")]
+
+
+class _NwResult(C.Structure):
+    _fields_ = [("op_off", C.c_void_p), ("ops", C.c_void_p)]
+
+
+class _MapResult(C.Structure):
+    _fields_ = [("reads", C.c_void_p), ("n_reads", C.c_int32), ("reports", C.c_void_p), ("n_reports", C.c_int64),
+                ("cigars", C.c_void_p), ("n_cigar_bytes", C.c_int64), ("junctions", C.c_void_p), ("n_junctions", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = ([(n, C.c_double) for n in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_h2d",
+                                           "ms_d2h", "ms_total_device", "ms_host")] +
+                [(n, C.c_uint64) for n in ("kernel_launches", "ext_steps", "ext_blocks", "lf_steps", "hits", "seeds",
+                                           "read_bases", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases",
+                                           "kmer_read_bases", "h2d_bytes", "d2h_bytes")])
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+KMER_JOB = np.dtype([("frag_off", "<i8"), ("frag_len", "<i4"), ("glen", "<i4"), ("gpos", "<i8")])
+KMER_HIT = np.dtype([("rpos", "<i4"), ("gpos", "<i4"), ("len", "<i4")])
+NW_JOB = np.dtype([("frag_off", "<i8"), ("m", "<i4"), ("n", "<i4"), ("gpos", "<i8")])
+READ_RESULT = np.dtype([("mapq", "<i4"), ("score", "<i4"), ("sub_score", "<i4"), ("mis_num", "<i4"),
+                        ("n_reports", "<i4"), ("best", "<i4"), ("report_off", "<i8")])
+REPORT = np.dtype([("aln_score", "<i4"), ("sj_type", "<i4"), ("flag", "<i4"), ("paired_idx", "<i4"), ("dir", "<i4"),
+                   ("chr_idx", "<i4"), ("pos", "<i8"), ("cigar_off", "<i8"), ("cigar_len", "<i4"), ("reserved", "<i4")])
+JUNCTION = np.dtype([("g1", "<i8"), ("g2", "<i8"), ("type", "<i4"), ("read", "<i4")])
+
+# every symbol include/dartgpu.h declares (tests check the library exports all of them)
+EXPORTS = ["dartgpu_default_params", "dartgpu_create", "dartgpu_create_from_files", "dartgpu_destroy",
+           "dartgpu_set_params", "dartgpu_last_error", "dartgpu_genome_size", "dartgpu_num_sequences",
+           "dartgpu_sequence_name", "dartgpu_sequence_length", "dartgpu_set_stream", "dartgpu_seed_and_cluster",
+           "dartgpu_kmer_reseed", "dartgpu_nw_align", "dartgpu_map_reads", "dartgpu_get_stats",
+           "dartgpu_upload_reads", "dartgpu_seed_and_cluster_resident", "dartgpu_synchronize",
+           "dartgpu_map_reads_resident"]
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise DartGpuError(-1, f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                               "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.dartgpu_default_params.argtypes = [C.POINTER(Params)]
+    L.dartgpu_create_from_files.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.POINTER(Params)]
+    L.dartgpu_destroy.argtypes = [C.c_void_p]
+    L.dartgpu_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.dartgpu_last_error.restype = C.c_char_p
+    L.dartgpu_last_error.argtypes = [C.c_void_p]
+    L.dartgpu_genome_size.restype = C.c_int64
+    L.dartgpu_genome_size.argtypes = [C.c_void_p]
+    L.dartgpu_num_sequences.argtypes = [C.c_void_p]
+    L.dartgpu_sequence_name.restype = C.c_char_p
+    L.dartgpu_sequence_name.argtypes = [C.c_void_p, C.c_int]
+    L.dartgpu_sequence_length.restype = C.c_int64
+    L.dartgpu_sequence_length.argtypes = [C.c_void_p, C.c_int]
+    L.dartgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.dartgpu_seed_and_cluster.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_Seeds)]
+    L.dartgpu_kmer_reseed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.dartgpu_nw_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(_NwResult)]
+    L.dartgpu_map_reads.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
+    L.dartgpu_map_reads_resident.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
+    L.dartgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.dartgpu_upload_reads.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.dartgpu_seed_and_cluster_resident.argtypes = [C.c_void_p]
+    L.dartgpu_synchronize.argtypes = [C.c_void_p]
+    return L
+
+
+def _view(ptr, dtype, n):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (int(n) * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+@dataclass
+class ReadBatch:
+    """Concatenated ASCII bases + offsets, as ReadItem_t.seq holds them (mate 2 already reverse-complemented)."""
+    bases: np.ndarray    # uint8
+    offsets: np.ndarray  # int64, n+1
+
+    @staticmethod
+    def from_list(seqs) -> "ReadBatch":
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+        return ReadBatch(bases, off)
+
+    @staticmethod
+    def from_codes(codes: np.ndarray) -> "ReadBatch":
+        """(n, L) array of codes 0..3 -> batch of equal-length reads."""
+        n, L = codes.shape
+        bases = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].reshape(-1).copy()
+        return ReadBatch(bases, np.arange(n + 1, dtype=np.int64) * L)
+
+    @property
+    def n(self) -> int:
+        return len(self.offsets) - 1
+
+    def _c(self) -> _Reads:
+        self.bases = np.ascontiguousarray(self.bases, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(self.offsets, dtype=np.int64)
+        return _Reads(self.n, self.bases.ctypes.data, self.offsets.ctypes.data)
+
+
+class Mapper:
+    """One context = one host thread on one GPU, index resident in that GPU's HBM."""
+
+    def __init__(self, index_prefix: str, device: int = 0, **params):
+        self.L = load_library()
+        self.params = Params()
+        self.L.dartgpu_default_params(C.byref(self.params))
+        for k, v in params.items():
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        rc = self.L.dartgpu_create_from_files(C.byref(self.h), device, index_prefix.encode(), C.byref(self.params))
+        if rc != 0:
+            raise DartGpuError(rc, self.L.dartgpu_last_error(None).decode())
+        self.G = self.L.dartgpu_genome_size(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dartgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DartGpuError(rc, self.L.dartgpu_last_error(self.h).decode())
+
+    def set_params(self, **params):
+        for k, v in params.items():
+            setattr(self.params, k, v)
+        self._check(self.L.dartgpu_set_params(self.h, C.byref(self.params)))
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self.L.dartgpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sequences(self):
+        return [(self.L.dartgpu_sequence_name(self.h, i).decode(), self.L.dartgpu_sequence_length(self.h, i))
+                for i in range(self.L.dartgpu_num_sequences(self.h))]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self.L.dartgpu_get_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    # ---- IdentifySeedPairs + GenerateAlignmentCandidate ----
+    def identify_seed_pairs(self, reads: ReadBatch) -> dict:
+        out = _Seeds()
+        self._check(self.L.dartgpu_seed_and_cluster(self.h, C.byref(reads._c()), C.byref(out)))
+        n = reads.n
+        seed_off = _view(out.seed_off, np.int64, n + 1).copy()
+        cand_off = _view(out.cand_off, np.int64, n + 1).copy()
+        ns, nc = int(seed_off[-1]), int(cand_off[-1])
+        return dict(seed_off=seed_off, cand_off=cand_off,
+                    seed_gpos=_view(out.seed_gpos, np.int64, ns).copy(), seed_rpos=_view(out.seed_rpos, np.int32, ns).copy(),
+                    seed_len=_view(out.seed_len, np.int32, ns).copy(), cand_begin=_view(out.cand_begin, np.int32, nc).copy(),
+                    cand_count=_view(out.cand_count, np.int32, nc).copy(), cand_score=_view(out.cand_score, np.int32, nc).copy())
+
+    def upload_reads(self, reads: ReadBatch):
+        self._check(self.L.dartgpu_upload_reads(self.h, C.byref(reads._c())))
+
+    def seed_resident(self):
+        self._check(self.L.dartgpu_seed_and_cluster_resident(self.h))
+
+    def synchronize(self):
+        self._check(self.L.dartgpu_synchronize(self.h))
+
+    # ---- GenerateLongestSimplePairsFromFragmentPair ----
+    def kmer_reseed(self, bases: bytes, jobs) -> np.ndarray:
+        """jobs: iterable of (frag_off, frag_len, gpos, glen). Returns KMER_HIT records (rpos, gpos, len)."""
+        arr = np.array([(o, l, gl, g) for (o, l, g, gl) in jobs], dtype=KMER_JOB)
+        b = np.frombuffer(bases, dtype=np.uint8)
+        out = C.c_void_p()
+        self._check(self.L.dartgpu_kmer_reseed(self.h, b.ctypes.data if len(b) else None, len(b),
+                                               arr.ctypes.data if len(arr) else None, len(arr), C.byref(out)))
+        return _view(out.value, KMER_HIT, len(arr)).copy()
+
+    # ---- nw_alignment ----
+    def nw_alignment(self, bases: bytes, jobs) -> list:
+        """jobs: iterable of (frag_off, m, gpos, n). Returns one uint8 op array per job (0 both, 1 gap in read, 2 gap in genome)."""
+        arr = np.array([(o, m, n, g) for (o, m, g, n) in jobs], dtype=NW_JOB)
+        b = np.frombuffer(bases, dtype=np.uint8)
+        out = _NwResult()
+        self._check(self.L.dartgpu_nw_align(self.h, b.ctypes.data if len(b) else None, len(b),
+                                            arr.ctypes.data if len(arr) else None, len(arr), C.byref(out)))
+        off = _view(out.op_off, np.int64, len(arr) + 1).copy()
+        ops = _view(out.ops, np.uint8, int(off[-1]) if len(off) else 0).copy()
+        return [ops[off[i]:off[i + 1]] for i in range(len(arr))]
+
+    # ---- the per-read loop body of ReadMapping ----
+    def map_reads(self, reads: ReadBatch, resident: bool = False, copy: bool = True) -> dict:
+        out = _MapResult()
+        fn = self.L.dartgpu_map_reads_resident if resident else self.L.dartgpu_map_reads
+        self._check(fn(self.h, C.byref(reads._c()), C.byref(out)))
+        if not copy:  # views into context-owned memory, valid until the next call
+            return dict(reads=_view(out.reads, READ_RESULT, out.n_reads), reports=_view(out.reports, REPORT, out.n_reports),
+                        n_cigar_bytes=out.n_cigar_bytes, junctions=_view(out.junctions, JUNCTION, out.n_junctions))
+        return dict(reads=_view(out.reads, READ_RESULT, out.n_reads).copy(),
+                    reports=_view(out.reports, REPORT, out.n_reports).copy(),
+                    cigars=_view(out.cigars, np.uint8, out.n_cigar_bytes).tobytes(),
+                    junctions=_view(out.junctions, JUNCTION, out.n_junctions).copy())

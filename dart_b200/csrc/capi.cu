@@ -1,0 +1,628 @@
+// C-ABI glue (include/dartgpu.h): context life cycle, index hand-over, stage runners.
+// There is deliberately no CPU implementation behind any entry point: without a CUDA device
+// dartgpu_create* fails with DARTGPU_ERR_NO_DEVICE and nothing else can be called.
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <new>
+
+#include "context.h"
+
+using namespace dartgpu;
+
+namespace dartgpu {
+
+static uint8_t *make_code_table()
+{
+    static uint8_t t[256];
+    for (int i = 0; i < 256; i++) t[i] = CODE_OTHER;
+    t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+    t['N'] = CODE_N; // only the upper-case literal breaks an 8-mer (/root/reference/src/KmerAnalysis.cpp:44)
+    return t;
+}
+static const uint8_t *g_code_table = make_code_table();
+static inline uint8_t code_of(unsigned char ch) { return g_code_table[ch]; }
+
+static thread_local std::string g_create_error;
+
+static int fail(dartgpu_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <class F> static int guarded(dartgpu_ctx *c, F &&f)
+{
+    try {
+        if (c) { cudaError_t e = cudaSetDevice(c->device); if (e != cudaSuccess) throw CudaError{e, "cudaSetDevice", __FILE__, __LINE__}; }
+        f();
+        return DARTGPU_OK;
+    } catch (const CudaError &e) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line, e.what);
+        cudaGetLastError();
+        return fail(c, e.e == cudaErrorNoDevice || e.e == cudaErrorInsufficientDriver ? DARTGPU_ERR_NO_DEVICE : DARTGPU_ERR_CUDA, buf);
+    } catch (const std::bad_alloc &) {
+        return fail(c, DARTGPU_ERR_NOMEM, "out of host memory");
+    } catch (const std::pair<int, std::string> &e) {
+        return fail(c, e.first, e.second);
+    } catch (const std::exception &e) {
+        return fail(c, DARTGPU_ERR_ARG, e.what());
+    }
+}
+
+void stats_begin(dartgpu_ctx *c)
+{
+    c->stats = dartgpu_stats{};
+    DG_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(DevStats), c->stream));
+}
+
+void add_ms(dartgpu_ctx *c, double *slot, cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) *slot += ms;
+    (void)c;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// read batch: encode + upload.  Every read starts on a 16-byte boundary so a lane stages 16 bases per load.
+// ---------------------------------------------------------------------------------------------------
+void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
+{
+    const int n = reads->n_reads;
+    if (n < 0 || (n > 0 && (!reads->bases || !reads->offsets))) throw std::make_pair(DARTGPU_ERR_ARG, std::string("bad read batch"));
+    c->h_dev_off.reserve(n + 1);
+    c->h_rlen.reserve(n + 1);
+    int64_t off = 0;
+    int max_rlen = 0;
+    for (int i = 0; i < n; i++) {
+        int64_t rl = reads->offsets[i + 1] - reads->offsets[i];
+        if (rl < 0) throw std::make_pair(DARTGPU_ERR_ARG, std::string("read offsets are not monotone"));
+        if (rl > DARTGPU_MAX_RLEN) throw std::make_pair(DARTGPU_ERR_READ_TOO_LONG, std::string("a read is longer than DARTGPU_MAX_RLEN"));
+        c->h_dev_off.p[i] = off;
+        c->h_rlen.p[i] = (int32_t)rl;
+        max_rlen = std::max(max_rlen, (int)rl);
+        off += (rl + 15) & ~(int64_t)15;
+    }
+    c->h_dev_off.p[n] = off;
+    c->h_codes.reserve(off + 16);
+    const int threads = c->prm.host_threads > 0 ? c->prm.host_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < n; i++) {
+        const char *s = reads->bases + reads->offsets[i];
+        uint8_t *d = c->h_codes.p + c->h_dev_off.p[i];
+        int rl = c->h_rlen.p[i], padded = (rl + 15) & ~15;
+        for (int k = 0; k < rl; k++) d[k] = code_of((unsigned char)s[k]);
+        for (int k = rl; k < padded; k++) d[k] = CODE_OTHER;
+    }
+    c->n_reads = n; c->max_rlen = max_rlen; c->n_code_bytes = off;
+    c->cap_rec = std::max(1, (max_rlen + 15) / 16);
+    c->d_codes.reserve(off + 16);
+    c->d_dev_off.reserve(n + 1);
+    c->d_rlen.reserve(n + 1);
+    cudaStream_t st = c->stream;
+    DG_CUDA(cudaEventRecord(c->ev[0], st));
+    if (n) {
+        DG_CUDA(cudaMemcpyAsync(c->d_codes.p, c->h_codes.p, off, cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemcpyAsync(c->d_dev_off.p, c->h_dev_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemcpyAsync(c->d_rlen.p, c->h_rlen.p, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    DG_CUDA(cudaEventRecord(c->ev[1], st));
+    c->stats.h2d_bytes += off + (n + 1) * 8 + n * 4;
+    c->stats.read_bases = 0;
+    for (int i = 0; i < n; i++) c->stats.read_bases += c->h_rlen.p[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 1
+// ---------------------------------------------------------------------------------------------------
+void run_seeding(dartgpu_ctx *c, bool fetch)
+{
+    const int n = c->n_reads;
+    cudaStream_t st = c->stream;
+    c->total_seeds = 0;
+    if (n == 0) { c->o_cand_off.assign(1, 0); c->h_seed_off.reserve(1); c->h_seed_off.p[0] = 0; return; }
+    c->d_recs.reserve((size_t)n * c->cap_rec);
+    c->d_nrec.reserve(n + 1); c->d_nhits.reserve(n + 1); c->d_ncand.reserve(n + 1);
+    c->d_seed_off.reserve(n + 2);
+    c->d_big_list.reserve(n + 1); c->d_big_count.reserve(4);
+    size_t tmp = scan_tmp_bytes(n);
+    c->d_scan_tmp.reserve(tmp + 256);
+
+    SeedLaunch a{};
+    a.codes = c->d_codes.p; a.dev_off = c->d_dev_off.p; a.rlen = c->d_rlen.p; a.n_reads = n;
+    a.cap_rec = c->cap_rec; a.max_dup = c->prm.max_dup; a.max_gaps = c->prm.max_gaps; a.max_intron = c->prm.max_intron;
+    a.recs = c->d_recs.p; a.nrec = c->d_nrec.p; a.nhits = c->d_nhits.p; a.seed_off = c->d_seed_off.p;
+    a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = c->d_big_count.p;
+    a.stats = c->d_stats.p;
+
+    DG_CUDA(cudaMemsetAsync(c->d_nhits.p + n, 0, sizeof(uint32_t), st));
+    DG_CUDA(cudaEventRecord(c->ev[2], st));
+    launch_search(c->ix, a, st);
+    DG_CUDA(cudaGetLastError());
+    DG_CUDA(cudaEventRecord(c->ev[3], st));
+    launch_scan_hits(a, c->d_scan_tmp.p, tmp, st);
+    DG_CUDA(cudaMemcpyAsync(c->h_total.p, c->d_seed_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    const int64_t total = c->h_total.p[0];
+    c->total_seeds = total;
+    c->stats.kernel_launches += 2;
+
+    c->d_keys.reserve(total + 1); c->d_meta.reserve(total + 1);
+    c->d_cand_begin.reserve(total + 1); c->d_cand_count.reserve(total + 1); c->d_cand_score.reserve(total + 1);
+    // reads with more seeds than fit the shared-memory sort need global scratch: bound = cap_rec * max_dup
+    size_t bound = (size_t)c->cap_rec * c->prm.max_dup, per_cta = 0;
+    if (bound > 4096) { per_cta = 64; while (per_cta < bound) per_cta <<= 1; c->d_big_scratch.reserve(per_cta * 148); }
+    a.keys = c->d_keys.p; a.meta = c->d_meta.p;
+    a.cand_begin = c->d_cand_begin.p; a.cand_count = c->d_cand_count.p; a.cand_score = c->d_cand_score.p;
+    a.big_scratch = c->d_big_scratch.p; a.big_scratch_per_cta = per_cta;
+
+    DG_CUDA(cudaEventRecord(c->ev[4], st));
+    launch_expand_locate(c->ix, a, total, st);
+    DG_CUDA(cudaGetLastError());
+    DG_CUDA(cudaEventRecord(c->ev[5], st));
+    launch_sort_cluster(c->ix, a, st);
+    DG_CUDA(cudaGetLastError());
+    DG_CUDA(cudaEventRecord(c->ev[6], st));
+    c->stats.kernel_launches += (total > 0 ? 2 : 0) + 2;
+
+    if (fetch) {
+        c->h_seed_off.reserve(n + 1); c->h_ncand.reserve(n + 1);
+        c->h_keys.reserve(total + 1);
+        c->h_cand_begin.reserve(total + 1); c->h_cand_count.reserve(total + 1); c->h_cand_score.reserve(total + 1);
+        DG_CUDA(cudaMemcpyAsync(c->h_seed_off.p, c->d_seed_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaMemcpyAsync(c->h_ncand.p, c->d_ncand.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (total) {
+            DG_CUDA(cudaMemcpyAsync(c->h_keys.p, c->d_keys.p, total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            DG_CUDA(cudaMemcpyAsync(c->h_cand_begin.p, c->d_cand_begin.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            DG_CUDA(cudaMemcpyAsync(c->h_cand_count.p, c->d_cand_count.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            DG_CUDA(cudaMemcpyAsync(c->h_cand_score.p, c->d_cand_score.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+        c->stats.d2h_bytes += (n + 1) * 8 + n * 4 + total * 20;
+    }
+    DG_CUDA(cudaMemcpyAsync(c->h_dstats.p, c->d_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaEventRecord(c->ev[7], st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    add_ms(c, &c->stats.ms_h2d, c->ev[0], c->ev[1]);
+    add_ms(c, &c->stats.ms_search, c->ev[2], c->ev[3]);
+    add_ms(c, &c->stats.ms_locate, c->ev[4], c->ev[5]);
+    add_ms(c, &c->stats.ms_sort_cluster, c->ev[5], c->ev[6]);
+    add_ms(c, &c->stats.ms_d2h, c->ev[6], c->ev[7]);
+    add_ms(c, &c->stats.ms_total_device, c->ev[2], c->ev[7]);
+    const DevStats &ds = c->h_dstats.p[0];
+    c->stats.ext_steps = ds.ext_steps; c->stats.ext_blocks = ds.ext_blocks; c->stats.lf_steps = ds.lf_steps;
+    c->stats.hits = ds.hits; c->stats.seeds = ds.seeds;
+    if (fetch) {
+        for (int i = 0; i < n; i++)
+            if (c->h_ncand.p[i] == 0xFFFFFFFFu) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("seed sort scratch overflow"));
+    }
+}
+
+static void unpack_seeds(dartgpu_ctx *c, dartgpu_seeds *out)
+{
+    const int n = c->n_reads;
+    const int64_t total = c->total_seeds;
+    c->o_seed_gpos.resize(total); c->o_seed_rpos.resize(total); c->o_seed_len.resize(total);
+    c->o_cand_off.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) c->o_cand_off[i + 1] = c->o_cand_off[i] + c->h_ncand.p[i];
+    const int64_t nc = c->o_cand_off[n];
+    c->o_cand_begin.resize(nc); c->o_cand_count.resize(nc); c->o_cand_score.resize(nc);
+    const int threads = c->prm.host_threads > 0 ? c->prm.host_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int64_t s = 0; s < total; s++) {
+        uint64_t k = c->h_keys.p[s];
+        c->o_seed_gpos[s] = key_gpos(k); c->o_seed_rpos[s] = key_rpos(k); c->o_seed_len[s] = key_len(k);
+    }
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < n; i++) {
+        int64_t so = c->h_seed_off.p[i], co = c->o_cand_off[i];
+        for (uint32_t k = 0; k < c->h_ncand.p[i]; k++) {
+            c->o_cand_begin[co + k] = c->h_cand_begin.p[so + k];
+            c->o_cand_count[co + k] = c->h_cand_count.p[so + k];
+            c->o_cand_score[co + k] = c->h_cand_score.p[so + k];
+        }
+    }
+    out->seed_off = c->h_seed_off.p;
+    out->seed_gpos = c->o_seed_gpos.data(); out->seed_rpos = c->o_seed_rpos.data(); out->seed_len = c->o_seed_len.data();
+    out->cand_off = c->o_cand_off.data();
+    out->cand_begin = c->o_cand_begin.data(); out->cand_count = c->o_cand_count.data(); out->cand_score = c->o_cand_score.data();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 2 / 3 runners
+// ---------------------------------------------------------------------------------------------------
+void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, int n_jobs, int max_len1)
+{
+    cudaStream_t st = c->stream;
+    c->h_khits.reserve(n_jobs + 1);
+    if (n_jobs == 0) return;
+    c->d_kjobs.reserve(n_jobs); c->d_khits.reserve(n_jobs);
+    DG_CUDA(cudaMemcpyAsync(c->d_kjobs.p, jobs, (size_t)n_jobs * sizeof(KmerJobDev), cudaMemcpyHostToDevice, st));
+    DG_CUDA(cudaEventRecord(c->ev[8], st));
+    launch_kmer(c->ix, codes_dev, c->d_kjobs.p, n_jobs, max_len1, c->d_khits.p, st);
+    DG_CUDA(cudaGetLastError());
+    DG_CUDA(cudaEventRecord(c->ev[9], st));
+    DG_CUDA(cudaMemcpyAsync(c->h_khits.p, c->d_khits.p, (size_t)n_jobs * sizeof(dartgpu_kmer_hit), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
+    c->stats.kernel_launches += 1;
+    c->stats.kmer_jobs += n_jobs;
+    for (int i = 0; i < n_jobs; i++) { c->stats.kmer_window_bases += jobs[i].len2; c->stats.kmer_read_bases += jobs[i].len1; }
+    c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(KmerJobDev);
+    c->stats.d2h_bytes += (uint64_t)n_jobs * sizeof(dartgpu_kmer_hit);
+}
+
+void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs)
+{
+    cudaStream_t st = c->stream;
+    c->o_op_off.assign(n_jobs + 1, 0);
+    c->o_ops.clear();
+    if (n_jobs == 0) return;
+    int64_t ops_total = 0, flag_total = 0;
+    int max_n = 0;
+    bool multi_strip = false;
+    for (int i = 0; i < n_jobs; i++) {
+        jobs[i].op_off = ops_total; jobs[i].flag_off = flag_total;
+        ops_total += jobs[i].m + jobs[i].n;
+        flag_total += (int64_t)jobs[i].m * ((jobs[i].n + 15) >> 4);
+        max_n = std::max(max_n, jobs[i].n);
+        multi_strip |= jobs[i].m > 32;
+        c->stats.nw_cells += (uint64_t)jobs[i].m * jobs[i].n;
+    }
+    c->stats.nw_jobs += n_jobs;
+    size_t rb_per_warp = multi_strip ? (size_t)2 * (max_n + 1) : 0;
+    c->d_njobs.reserve(n_jobs); c->d_nw_flags.reserve(flag_total + 1); c->d_nw_ops.reserve(ops_total + 1);
+    c->d_nw_nops.reserve(n_jobs);
+    c->d_nw_rowbuf.reserve(rb_per_warp * nw_grid_warps() + 1);
+    c->h_nw_ops.reserve(ops_total + 1); c->h_nw_nops.reserve(n_jobs);
+    DG_CUDA(cudaMemcpyAsync(c->d_njobs.p, jobs, (size_t)n_jobs * sizeof(NwJobDev), cudaMemcpyHostToDevice, st));
+    DG_CUDA(cudaEventRecord(c->ev[10], st));
+    launch_nw(c->ix, codes_dev, c->d_njobs.p, n_jobs, c->d_nw_flags.p, c->d_nw_rowbuf.p, rb_per_warp, c->d_nw_ops.p, c->d_nw_nops.p, st);
+    DG_CUDA(cudaGetLastError());
+    DG_CUDA(cudaEventRecord(c->ev[11], st));
+    DG_CUDA(cudaMemcpyAsync(c->h_nw_ops.p, c->d_nw_ops.p, ops_total, cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaMemcpyAsync(c->h_nw_nops.p, c->d_nw_nops.p, (size_t)n_jobs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
+    c->stats.kernel_launches += 1;
+    c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(NwJobDev);
+    c->stats.d2h_bytes += ops_total + (uint64_t)n_jobs * 4;
+    for (int i = 0; i < n_jobs; i++) c->o_op_off[i + 1] = c->o_op_off[i] + c->h_nw_nops.p[i];
+    c->o_ops.resize(c->o_op_off[n_jobs]);
+    const int threads = c->prm.host_threads > 0 ? c->prm.host_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < n_jobs; i++) {
+        int k = c->h_nw_nops.p[i];
+        const uint8_t *src = c->h_nw_ops.p + jobs[i].op_off + jobs[i].m + jobs[i].n - k; // written right-aligned by the traceback
+        if (k) memcpy(c->o_ops.data() + c->o_op_off[i], src, k);
+    }
+}
+
+// fragment bases of the stage entry points -> device codes
+static const uint8_t *upload_job_bases(dartgpu_ctx *c, const char *bases, int64_t n_bases)
+{
+    c->h_job_codes.reserve(n_bases + 16); c->d_job_codes.reserve(n_bases + 16);
+    for (int64_t i = 0; i < n_bases; i++) c->h_job_codes.p[i] = code_of((unsigned char)bases[i]);
+    if (n_bases) DG_CUDA(cudaMemcpyAsync(c->d_job_codes.p, c->h_job_codes.p, n_bases, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += n_bases;
+    return c->d_job_codes.p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// index hand-over
+// ---------------------------------------------------------------------------------------------------
+static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
+{
+    if (!v || !v->bwt || !v->sa || !v->pac || v->n_seqs <= 0 || !v->seq_len_arr)
+        throw std::make_pair(DARTGPU_ERR_ARG, std::string("incomplete index view"));
+    if (v->sa_intv == 0 || (v->sa_intv & (v->sa_intv - 1)))
+        throw std::make_pair(DARTGPU_ERR_INDEX, std::string("SA sampling interval is not a power of two"));
+    if (v->seq_len != 2 * (uint64_t)v->l_pac)
+        throw std::make_pair(DARTGPU_ERR_INDEX, std::string("index is not a forward+reverse-complement (FMD) index"));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); throw std::make_pair(DARTGPU_ERR_NO_DEVICE, std::string("no CUDA device: libdartgpu has no CPU fallback")); }
+    if (c->device < 0 || c->device >= ndev) throw std::make_pair(DARTGPU_ERR_ARG, std::string("device ordinal out of range"));
+    DG_CUDA(cudaSetDevice(c->device));
+    DG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev) DG_CUDA(cudaEventCreate(&ev));
+    cudaStream_t st = c->stream;
+
+    c->G = v->l_pac;
+    int64_t acc = 0;
+    std::vector<std::pair<int64_t, int>> ends;
+    for (int i = 0; i < v->n_seqs; i++) {
+        c->names.push_back(v->seq_names && v->seq_names[i] ? v->seq_names[i] : ("seq" + std::to_string(i)));
+        c->chr_len.push_back(v->seq_len_arr[i]);
+        c->chr_fwd.push_back(acc);
+        acc += v->seq_len_arr[i];
+        ends.push_back({c->chr_fwd[i] + v->seq_len_arr[i] - 1, i});          // forward copy
+        ends.push_back({2 * c->G - acc + v->seq_len_arr[i] - 1, i});         // reverse-complement copy
+    }
+    std::sort(ends.begin(), ends.end());
+    for (auto &p : ends) { c->ends.push_back(p.first); c->end_chr.push_back(p.second); }
+    c->pac.assign(v->pac, v->pac + v->l_pac / 4 + 1);
+
+    // Occ blocks: raw words up, re-laid-out on the device
+    const uint64_t n_blocks = (v->seq_len + 127) / 128;
+    if (v->bwt_size < n_blocks * 16 - 8) throw std::make_pair(DARTGPU_ERR_INDEX, std::string(".bwt is shorter than its header implies"));
+    {
+        DevBuf<uint32_t> raw;
+        raw.reserve(n_blocks * 16 + 16);
+        DG_CUDA(cudaMemsetAsync(raw.p, 0, (n_blocks * 16 + 16) * 4, st));
+        DG_CUDA(cudaMemcpyAsync(raw.p, v->bwt, std::min<uint64_t>(v->bwt_size, n_blocks * 16 + 16) * 4, cudaMemcpyHostToDevice, st));
+        c->d_occ.reserve(n_blocks * 4);
+        launch_relayout_occ(raw.p, c->d_occ.p, n_blocks, st);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaStreamSynchronize(st));
+    }
+    c->d_sa.reserve(v->n_sa);
+    DG_CUDA(cudaMemcpyAsync(c->d_sa.p, v->sa, v->n_sa * 8, cudaMemcpyHostToDevice, st));
+    {
+        DevBuf<uint8_t> dpac;
+        dpac.reserve(c->pac.size());
+        DG_CUDA(cudaMemcpyAsync(dpac.p, c->pac.data(), c->pac.size(), cudaMemcpyHostToDevice, st));
+        c->d_ref2.reserve((2 * c->G + 15) / 16 + 2);
+        launch_build_ref2(dpac.p, c->d_ref2.p, c->G, st);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaStreamSynchronize(st));
+    }
+    c->d_ends.reserve(c->ends.size());
+    DG_CUDA(cudaMemcpyAsync(c->d_ends.p, c->ends.data(), c->ends.size() * 8, cudaMemcpyHostToDevice, st));
+    c->d_stats.reserve(1); c->h_total.reserve(2); c->h_dstats.reserve(1);
+    DG_CUDA(cudaStreamSynchronize(st));
+
+    DevIndex &ix = c->ix;
+    ix.occ = c->d_occ.p; ix.n_blocks = n_blocks; ix.sa = c->d_sa.p;
+    ix.sa_mask = v->sa_intv - 1; ix.sa_shift = 0;
+    while ((1ull << ix.sa_shift) < v->sa_intv) ix.sa_shift++;
+    ix.primary = v->primary; ix.seq_len = v->seq_len;
+    for (int i = 0; i < 5; i++) ix.L2[i] = v->L2[i];
+    ix.ref2 = c->d_ref2.p; ix.G = c->G; ix.chr_ends = c->d_ends.p; ix.n_ends = (int)c->ends.size();
+}
+
+static bool slurp(const std::string &fn, std::vector<uint8_t> &buf)
+{
+    FILE *fp = fopen(fn.c_str(), "rb");
+    if (!fp) return false;
+    fseek(fp, 0, SEEK_END);
+    long n = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    buf.resize(n);
+    size_t got = n ? fread(buf.data(), 1, n, fp) : 0;
+    fclose(fp);
+    return got == (size_t)n;
+}
+
+} // namespace dartgpu
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+extern "C" {
+
+void dartgpu_default_params(dartgpu_params *p)
+{
+    if (!p) return;
+    p->max_gaps = 5; p->max_intron = 500000; p->min_intron = 5; p->max_mismatch = 0; p->max_dup = 100;
+    p->multi_hit = 0; p->pair_end = 0; p->all_sj = 0; p->unique = 0; p->host_threads = 0;
+}
+
+static void sanitize(dartgpu_params &p)
+{   // the clamps of the reference's flag parser (/root/reference/src/main.cpp:173-178, :187)
+    if (p.max_dup < 100) p.max_dup = 100; else if (p.max_dup >= 10000) p.max_dup = 10000;
+    if (p.max_intron < 100000) p.max_intron = 100000;
+}
+
+int dartgpu_create(dartgpu_ctx **out, int device, const dartgpu_index_view *idx, const dartgpu_params *p)
+{
+    if (!out) return fail(nullptr, DARTGPU_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    dartgpu_ctx *c = new (std::nothrow) dartgpu_ctx;
+    if (!c) return fail(nullptr, DARTGPU_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    if (p) c->prm = *p; else dartgpu_default_params(&c->prm);
+    sanitize(c->prm);
+    int rc = guarded(nullptr, [&] { build_context(c, idx); });
+    if (rc != DARTGPU_OK) { dartgpu_destroy(c); return rc; }
+    *out = c;
+    return DARTGPU_OK;
+}
+
+int dartgpu_create_from_files(dartgpu_ctx **out, int device, const char *prefix, const dartgpu_params *p)
+{
+    if (!out || !prefix) return fail(nullptr, DARTGPU_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    std::vector<uint8_t> bwt, sa, pac;
+    std::string pre(prefix);
+    if (!slurp(pre + ".bwt", bwt) || bwt.size() < 40) return fail(nullptr, DARTGPU_ERR_INDEX, "cannot read " + pre + ".bwt");
+    if (!slurp(pre + ".sa", sa) || sa.size() < 56) return fail(nullptr, DARTGPU_ERR_INDEX, "cannot read " + pre + ".sa");
+    if (!slurp(pre + ".pac", pac)) return fail(nullptr, DARTGPU_ERR_INDEX, "cannot read " + pre + ".pac");
+    dartgpu_index_view v{};
+    memcpy(&v.primary, bwt.data(), 8);
+    memcpy(&v.L2[1], bwt.data() + 8, 32);
+    v.L2[0] = 0;
+    v.seq_len = v.L2[4];
+    v.bwt_size = (bwt.size() - 40) / 4;
+    v.bwt = reinterpret_cast<const uint32_t *>(bwt.data() + 40);
+    memcpy(&v.sa_intv, sa.data() + 40, 8);
+    if (v.sa_intv == 0) return fail(nullptr, DARTGPU_ERR_INDEX, pre + ".sa: bad sampling interval");
+    v.n_sa = (v.seq_len + v.sa_intv) / v.sa_intv;
+    if (sa.size() < 56 + (v.n_sa - 1) * 8) return fail(nullptr, DARTGPU_ERR_INDEX, pre + ".sa is truncated");
+    std::vector<uint64_t> sav(v.n_sa);
+    sav[0] = (uint64_t)-1;
+    memcpy(sav.data() + 1, sa.data() + 56, (v.n_sa - 1) * 8);
+    v.sa = sav.data();
+    FILE *fp = fopen((pre + ".ann").c_str(), "r");
+    if (!fp) return fail(nullptr, DARTGPU_ERR_INDEX, "cannot read " + pre + ".ann");
+    long long lpac; int nseq; unsigned seed;
+    std::vector<std::string> names; std::vector<int64_t> lens;
+    if (fscanf(fp, "%lld%d%u", &lpac, &nseq, &seed) != 3) { fclose(fp); return fail(nullptr, DARTGPU_ERR_INDEX, pre + ".ann: bad header"); }
+    for (int i = 0; i < nseq; i++) {
+        unsigned gi; char name[1024]; long long off; int len, namb;
+        if (fscanf(fp, "%u%1023s", &gi, name) != 2) break;
+        int ch; while ((ch = fgetc(fp)) != '\n' && ch != EOF) {}
+        if (fscanf(fp, "%lld%d%d", &off, &len, &namb) != 3) break;
+        names.push_back(name); lens.push_back(len);
+    }
+    fclose(fp);
+    if ((int)names.size() != nseq) return fail(nullptr, DARTGPU_ERR_INDEX, pre + ".ann: truncated");
+    std::vector<const char *> namep;
+    for (auto &s : names) namep.push_back(s.c_str());
+    v.l_pac = lpac; v.pac = pac.data(); v.n_seqs = nseq; v.seq_len_arr = lens.data(); v.seq_names = namep.data();
+    if ((int64_t)pac.size() < lpac / 4 + 1) return fail(nullptr, DARTGPU_ERR_INDEX, pre + ".pac is truncated");
+    return dartgpu_create(out, device, &v, p);
+}
+
+void dartgpu_destroy(dartgpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int dartgpu_set_params(dartgpu_ctx *c, const dartgpu_params *p)
+{
+    if (!c || !p) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    c->prm = *p; sanitize(c->prm);
+    return DARTGPU_OK;
+}
+const char *dartgpu_last_error(const dartgpu_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+int64_t dartgpu_genome_size(const dartgpu_ctx *c) { return c ? c->G : 0; }
+int dartgpu_num_sequences(const dartgpu_ctx *c) { return c ? (int)c->names.size() : 0; }
+const char *dartgpu_sequence_name(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->names.size()) ? c->names[i].c_str() : ""; }
+int64_t dartgpu_sequence_length(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->chr_len.size()) ? c->chr_len[i] : 0; }
+int dartgpu_set_stream(dartgpu_ctx *c, void *s)
+{
+    if (!c) return DARTGPU_ERR_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return DARTGPU_OK;
+}
+
+int dartgpu_seed_and_cluster(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_seeds *out)
+{
+    if (!c || !reads || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    return guarded(c, [&] {
+        Timer t;
+        stats_begin(c);
+        upload_reads(c, reads);
+        run_seeding(c, true);
+        unpack_seeds(c, out);
+        c->stats.ms_host = t.ms();
+    });
+}
+
+int dartgpu_upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
+{
+    if (!c || !reads) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    return guarded(c, [&] { stats_begin(c); upload_reads(c, reads); DG_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+int dartgpu_seed_and_cluster_resident(dartgpu_ctx *c)
+{
+    if (!c) return DARTGPU_ERR_ARG;
+    return guarded(c, [&] {
+        uint64_t rb = c->stats.read_bases;
+        stats_begin(c);
+        c->stats.read_bases = rb;
+        run_seeding(c, false);
+    });
+}
+
+int dartgpu_synchronize(dartgpu_ctx *c)
+{
+    if (!c) return DARTGPU_ERR_ARG;
+    return guarded(c, [&] { DG_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+int dartgpu_kmer_reseed(dartgpu_ctx *c, const char *bases, int64_t n_bases, const dartgpu_kmer_job *jobs, int32_t n_jobs,
+                        const dartgpu_kmer_hit **out)
+{
+    if (!c || !out || n_jobs < 0 || (n_jobs && (!jobs || !bases))) return fail(c, DARTGPU_ERR_ARG, "bad argument");
+    return guarded(c, [&] {
+        stats_begin(c);
+        const uint8_t *dcodes = upload_job_bases(c, bases, n_bases);
+        c->h_kjobs.reserve(n_jobs + 1);
+        int max1 = 8;
+        for (int i = 0; i < n_jobs; i++) {
+            const dartgpu_kmer_job &j = jobs[i];
+            if (j.frag_off < 0 || j.frag_len < 0 || j.frag_off + j.frag_len > n_bases || j.glen < 0 || j.gpos < 0 ||
+                j.gpos + j.glen > 2 * c->G)
+                throw std::make_pair(DARTGPU_ERR_ARG, std::string("k-mer job out of range"));
+            if (j.frag_len > DARTGPU_MAX_RLEN) throw std::make_pair(DARTGPU_ERR_READ_TOO_LONG, std::string("k-mer fragment too long"));
+            c->h_kjobs.p[i] = KmerJobDev{j.frag_off, j.gpos, j.frag_len, j.glen};
+            max1 = std::max(max1, j.frag_len);
+        }
+        run_kmer(c, dcodes, c->h_kjobs.p, n_jobs, max1);
+        *out = c->h_khits.p;
+    });
+}
+
+int dartgpu_nw_align(dartgpu_ctx *c, const char *bases, int64_t n_bases, const dartgpu_nw_job *jobs, int32_t n_jobs,
+                     dartgpu_nw_result *out)
+{
+    if (!c || !out || n_jobs < 0 || (n_jobs && (!jobs || !bases))) return fail(c, DARTGPU_ERR_ARG, "bad argument");
+    return guarded(c, [&] {
+        stats_begin(c);
+        const uint8_t *dcodes = upload_job_bases(c, bases, n_bases);
+        c->h_njobs.reserve(n_jobs + 1);
+        for (int i = 0; i < n_jobs; i++) {
+            const dartgpu_nw_job &j = jobs[i];
+            if (j.frag_off < 0 || j.m < 0 || j.frag_off + j.m > n_bases || j.n < 0 || j.gpos < 0 || j.gpos + j.n > 2 * c->G)
+                throw std::make_pair(DARTGPU_ERR_ARG, std::string("NW job out of range"));
+            c->h_njobs.p[i] = NwJobDev{j.frag_off, j.gpos, 0, 0, j.m, j.n};
+        }
+        run_nw(c, dcodes, c->h_njobs.p, n_jobs);
+        out->op_off = c->o_op_off.data();
+        out->ops = c->o_ops.data();
+    });
+}
+
+int dartgpu_map_reads(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out)
+{
+    if (!c || !reads || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (c->prm.pair_end && (reads->n_reads & 1)) return fail(c, DARTGPU_ERR_ARG, "paired-end batch with an odd number of reads");
+    return guarded(c, [&] {
+        Timer t;
+        stats_begin(c);
+        upload_reads(c, reads);
+        run_seeding(c, true);
+        double dev_before = c->stats.ms_kmer + c->stats.ms_nw;
+        (void)dev_before;
+        run_pipeline(c, reads, out);
+        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_h2d;
+        c->stats.ms_host = t.ms();
+    });
+}
+
+int dartgpu_map_reads_resident(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out)
+{
+    if (!c || !reads || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (reads->n_reads != c->n_reads) return fail(c, DARTGPU_ERR_ARG, "batch differs from the uploaded one");
+    if (c->prm.pair_end && (reads->n_reads & 1)) return fail(c, DARTGPU_ERR_ARG, "paired-end batch with an odd number of reads");
+    return guarded(c, [&] {
+        Timer t;
+        uint64_t rb = c->stats.read_bases;
+        stats_begin(c);
+        c->stats.read_bases = rb;
+        run_seeding(c, true);
+        run_pipeline(c, reads, out);
+        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw;
+        c->stats.ms_host = t.ms();
+    });
+}
+
+int dartgpu_get_stats(const dartgpu_ctx *c, dartgpu_stats *out)
+{
+    if (!c || !out) return DARTGPU_ERR_ARG;
+    *out = c->stats;
+    return DARTGPU_OK;
+}
+
+} // extern "C"

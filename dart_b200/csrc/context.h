@@ -1,0 +1,118 @@
+// The per-(host thread, GPU) context behind the C-ABI, and the internal stage runners the whole-path
+// orchestration (pipeline.cu) shares with the stage entry points (capi.cu).
+#pragma once
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "dartgpu_internal.h"
+
+struct dartgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    dartgpu_params prm{};
+    std::string err;
+
+    // ---- host-side view of the index (orchestration needs reference bases and the sequence table) ----
+    int64_t G = 0;
+    std::vector<std::string> names;
+    std::vector<int64_t> chr_len, chr_fwd;
+    std::vector<int64_t> ends;      // sorted ChrLocMap keys (/root/reference/src/bwt_index.cpp:249-250)
+    std::vector<int> end_chr;       // ChrLocMap values
+    std::vector<uint8_t> pac;       // forward strand, 2 bits per base
+
+    // ---- device-resident index ----
+    dartgpu::DevIndex ix{};
+    dartgpu::DevBuf<ulonglong2> d_occ;
+    dartgpu::DevBuf<uint64_t> d_sa;
+    dartgpu::DevBuf<uint32_t> d_ref2;
+    dartgpu::DevBuf<int64_t> d_ends;
+
+    // ---- read batch on the device ----
+    int n_reads = 0, max_rlen = 0, cap_rec = 0;
+    int64_t n_code_bytes = 0;
+    dartgpu::PinBuf<uint8_t> h_codes;
+    dartgpu::PinBuf<int64_t> h_dev_off;
+    dartgpu::PinBuf<int32_t> h_rlen;
+    dartgpu::DevBuf<uint8_t> d_codes;
+    dartgpu::DevBuf<int64_t> d_dev_off;
+    dartgpu::DevBuf<int32_t> d_rlen;
+
+    // ---- seeding buffers ----
+    dartgpu::DevBuf<dartgpu::SearchRec> d_recs;
+    dartgpu::DevBuf<uint32_t> d_nrec, d_nhits, d_ncand, d_meta, d_big_list, d_big_count;
+    dartgpu::DevBuf<int64_t> d_seed_off;
+    dartgpu::DevBuf<uint64_t> d_keys, d_big_scratch;
+    dartgpu::DevBuf<int32_t> d_cand_begin, d_cand_count, d_cand_score;
+    dartgpu::DevBuf<uint8_t> d_scan_tmp;
+    dartgpu::DevBuf<dartgpu::DevStats> d_stats;
+    dartgpu::PinBuf<int64_t> h_total;
+    dartgpu::PinBuf<dartgpu::DevStats> h_dstats;
+    int64_t total_seeds = 0;
+
+    // seeding results on the host
+    dartgpu::PinBuf<int64_t> h_seed_off;
+    dartgpu::PinBuf<uint64_t> h_keys;
+    dartgpu::PinBuf<int32_t> h_cand_begin, h_cand_count, h_cand_score;
+    dartgpu::PinBuf<uint32_t> h_ncand;
+    std::vector<int64_t> o_seed_gpos, o_cand_off;
+    std::vector<int32_t> o_seed_rpos, o_seed_len, o_cand_begin, o_cand_count, o_cand_score;
+
+    // ---- k-mer / NW job buffers ----
+    dartgpu::DevBuf<uint8_t> d_job_codes;         // fragment bases of the stage entry points
+    dartgpu::PinBuf<uint8_t> h_job_codes;
+    dartgpu::PinBuf<dartgpu::KmerJobDev> h_kjobs;
+    dartgpu::DevBuf<dartgpu::KmerJobDev> d_kjobs;
+    dartgpu::DevBuf<dartgpu_kmer_hit> d_khits;
+    dartgpu::PinBuf<dartgpu_kmer_hit> h_khits;
+    dartgpu::PinBuf<dartgpu::NwJobDev> h_njobs;
+    dartgpu::DevBuf<dartgpu::NwJobDev> d_njobs;
+    dartgpu::DevBuf<uint32_t> d_nw_flags;
+    dartgpu::DevBuf<int32_t> d_nw_rowbuf, d_nw_nops;
+    dartgpu::DevBuf<uint8_t> d_nw_ops;
+    dartgpu::PinBuf<uint8_t> h_nw_ops;
+    dartgpu::PinBuf<int32_t> h_nw_nops;
+    std::vector<int64_t> o_op_off;
+    std::vector<uint8_t> o_ops;
+
+    // ---- whole-path results ----
+    std::vector<dartgpu_read_result> o_reads;
+    std::vector<dartgpu_report> o_reports;
+    std::vector<char> o_cigars;
+    std::vector<dartgpu_junction> o_junctions;
+
+    // ---- measurement ----
+    dartgpu_stats stats{};
+    cudaEvent_t ev[16] = {};
+};
+
+namespace dartgpu {
+
+void stats_begin(dartgpu_ctx *c);
+void add_ms(dartgpu_ctx *c, double *slot, cudaEvent_t a, cudaEvent_t b);
+
+// stage runners; all throw CudaError / std::exception on failure
+void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads);          // encode + H2D
+void run_seeding(dartgpu_ctx *c, bool fetch_results);                    // search, locate, sort+cluster [, D2H + unpack]
+// k-mer jobs whose fragments live in `codes_dev` (device). Results in c->h_khits (valid after return).
+void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, int n_jobs, int max_len1);
+// NW jobs (op_off / flag_off are filled here). Results: c->o_op_off / c->o_ops (compacted, left-to-right columns).
+void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs);
+// the whole per-read path over the uploaded batch
+void run_pipeline(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out);
+
+inline int host_ref_code(const dartgpu_ctx *c, int64_t p)
+{
+    if (p < 0 || p >= 2 * c->G) return 0;
+    if (p < c->G) return (c->pac[p >> 2] >> ((~p & 3) << 1)) & 3;
+    int64_t q = 2 * c->G - 1 - p;
+    return 3 - ((c->pac[q >> 2] >> ((~q & 3) << 1)) & 3);
+}
+inline char host_ref_char(const dartgpu_ctx *c, int64_t p) { return "ACGT"[host_ref_code(c, p)]; }
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+} // namespace dartgpu

@@ -1,0 +1,433 @@
+// Seeding on the GPU: FM-index exact-match segment search, SA locate, per-read seed sort and
+// simple-pair clustering into alignment candidates.
+//
+// Replaces (bit-exactly) /root/reference/src/bwt_search.cpp:43-182 (bwt_occ4 / bwt_2occ4 / bwt_occ /
+// bwt_invPsi / bwt_sa / BWT_Search) and /root/reference/src/AlignmentCandidates.cpp:181-288
+// (IdentifySeedPairs, GenerateAlignmentCandidate).
+//
+// Execution model
+//   * a GROUP of 4 lanes owns one read at a time; 8 groups per warp run 8 independent FM chains.
+//     One rank query = one 128-bit load per lane = one 64-byte Occ block per group, each lane
+//     popcounting its own 32 symbols (3 POPC), combined with two xor-shuffles.
+//   * the nested loops of the reference (reads > search starts > extension steps) are flattened into a
+//     single loop whose every iteration performs exactly one rank step, so the 8 groups of a warp stay
+//     converged although their reads, search starts and match lengths differ.
+//   * reads are staged in shared memory 2-bit packed (+ a 1-bit "not ACGT" plane).
+//   * search only records SA intervals; after a prefix sum over the hit counts a second kernel resolves
+//     every hit with its own group (LF walk to the next SA sample), so repetitive reads do not serialise.
+//   * seeds are 64-bit keys (gPos | rPos | len): sorting the keys is the reference's CompByGenomePos order.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "dartgpu_internal.h"
+
+namespace dartgpu {
+
+constexpr int SEARCH_THREADS = 128;
+constexpr int GROUPS_PER_CTA = SEARCH_THREADS / 4;
+constexpr int RWORDS = DARTGPU_MAX_RLEN / 16;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------------
+// rank primitives
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fold_even(uint64_t x) { return (uint32_t)x | ((uint32_t)(x >> 32) << 1); }
+
+// A | C<<8 | G<<16 | T<<24 among the first n (0..32) symbols of a 32-symbol word (first symbol in the top bits)
+__device__ __forceinline__ uint32_t count_packed(uint64_t b, int n)
+{
+    const uint64_t M5 = 0x5555555555555555ull;
+    uint64_t keep = n > 0 ? (~0ull << (64 - 2 * n)) : 0ull;
+    uint64_t bk = b & keep;
+    uint64_t lo = bk & M5, hi = (bk >> 1) & M5;
+    int t = __popc(fold_even(hi & lo)), gt = __popc(fold_even(hi)), ct = __popc(fold_even(lo));
+    int g = gt - t, c = ct - t, a = n - gt - ct + t;
+    return (uint32_t)a | (uint32_t)c << 8 | (uint32_t)g << 16 | (uint32_t)t << 24;
+}
+
+__device__ __forceinline__ ulonglong2 load_quarter(const DevIndex &ix, uint64_t kk, int q)
+{
+    return __ldg(ix.occ + ((kk >> 7) << 2) + q);
+}
+
+// lane q of the group returns Occ(symbol q, kk) — number of q in BWT[0..kk], kk already sentinel-adjusted
+__device__ __forceinline__ uint64_t finish_rank(ulonglong2 v, uint64_t kk, int q, unsigned gmask)
+{
+    int n = (int)(kk & 127) + 1 - 32 * q;
+    n = max(0, min(32, n));
+    uint32_t pc = count_packed(v.y, n);
+    pc += __shfl_xor_sync(gmask, pc, 1);
+    pc += __shfl_xor_sync(gmask, pc, 2);
+    return v.x + ((pc >> (8 * q)) & 0xffu);
+}
+
+__device__ __forceinline__ int rd_code(const uint32_t *pk, int p) { return (pk[p >> 4] >> ((p & 15) * 2)) & 3; }
+__device__ __forceinline__ int rd_amb(const uint16_t *am, int p) { return (am[p >> 4] >> (p & 15)) & 1; }
+
+// stage one read in the group's shared-memory slot: 2 bits per base + 1 ambiguity bit per base
+__device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, int rl, uint32_t *pk, uint16_t *am,
+                                           int q, unsigned gmask)
+{
+    int nw = (rl + 15) >> 4;
+    __syncwarp(gmask);
+    for (int w = q; w < nw; w += 4) {
+        uint4 v = *reinterpret_cast<const uint4 *>(codes + off + 16 * (int64_t)w);
+        uint32_t x[4] = {v.x, v.y, v.z, v.w};
+        uint32_t p2 = 0, a = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t t = x[i];
+            uint32_t two = (t & 3u) | ((t >> 6) & 0xCu) | ((t >> 12) & 0x30u) | ((t >> 18) & 0xC0u);
+            uint32_t ab = ((t >> 2) & 1u) | ((t >> 9) & 2u) | ((t >> 16) & 4u) | ((t >> 23) & 8u);
+            p2 |= two << (8 * i);
+            a |= ab << (4 * i);
+        }
+        pk[w] = p2;
+        am[w] = (uint16_t)a;
+    }
+    __syncwarp(gmask);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel 1: maximal exact-match segment search (IdentifySeedPairs' loop around BWT_Search, without locate)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEARCH_THREADS)
+k_search(DevIndex ix, SeedLaunch a)
+{
+    __shared__ uint32_t s_pk[GROUPS_PER_CTA][RWORDS];
+    __shared__ uint16_t s_am[GROUPS_PER_CTA][RWORDS];
+
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const unsigned gmask = 0xFu << (lane & ~3);
+    const int grp = threadIdx.x >> 2;
+    uint32_t *pk = s_pk[grp];
+    uint16_t *am = s_am[grp];
+    const int stride = gridDim.x * GROUPS_PER_CTA;
+    int r = blockIdx.x * GROUPS_PER_CTA + grp;
+
+    bool have_read = false, searching = false;
+    int rl = 0, start = 0, p = 0;
+    uint32_t nr = 0, nh = 0;
+    uint64_t x0 = 0, x1 = 0, x2 = 0;
+    unsigned long long st_steps = 0, st_blocks = 0;
+
+    for (;;) {
+        if (!searching) {
+            bool done = false;
+            for (;;) {
+                if (!have_read) {
+                    if (r >= a.n_reads) { done = true; break; }
+                    rl = a.rlen[r];
+                    stage_read(a.codes, a.dev_off[r], rl, pk, am, q, gmask);
+                    start = 0; nr = 0; nh = 0; have_read = true;
+                }
+                while (start < rl - 13 && rd_amb(am, start)) start++;
+                if (start < rl - 13) break;
+                if (q == 0) { a.nrec[r] = nr; a.nhits[r] = nh; }
+                have_read = false;
+                r += stride;
+            }
+            if (done) break;
+            int c0 = rd_code(pk, start);
+            x0 = ix.L2[c0] + 1; x1 = ix.L2[3 - c0] + 1; x2 = ix.L2[c0 + 1] - ix.L2[c0];
+            p = start + 1;
+            searching = true;
+        }
+        // ---- one forward-extension step (bwt_2occ4 + interval update, bwt_search.cpp:152-170) ----
+        bool end = false;
+        if (p >= rl || rd_amb(am, p)) end = true;
+        else {
+            uint64_t k = x1 - 1, l = x1 - 1 + x2;
+            uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
+            ulonglong2 vk = load_quarter(ix, kk, q), vl = load_quarter(ix, ll, q);
+            st_steps++; st_blocks += ((kk >> 7) == (ll >> 7)) ? 1 : 2;
+            uint64_t tk = finish_rank(vk, kk, q, gmask), tl = finish_rank(vl, ll, q, gmask);
+            uint64_t n2 = tl - tk;
+            int c = 3 - rd_code(pk, p);
+            uint64_t n2c = __shfl_sync(gmask, n2, c, 4), tkc = __shfl_sync(gmask, tk, c, 4);
+            if (n2c == 0) end = true;
+            else {
+                uint64_t above = q > c ? n2 : 0;
+                above += __shfl_xor_sync(gmask, above, 1);
+                above += __shfl_xor_sync(gmask, above, 2);
+                x0 = x0 + ((x1 <= ix.primary && x1 + x2 - 1 >= ix.primary) ? 1 : 0) + above;
+                x1 = ix.L2[c] + 1 + tkc;
+                x2 = n2c;
+                p++;
+            }
+        }
+        if (end) {
+            int len = p - start;
+            if (x2 <= (uint64_t)a.max_dup && len >= 16) { // bwt_search.cpp:173
+                if (q == 0 && (int)nr < a.cap_rec) {
+                    SearchRec rec; rec.x0 = x0; rec.freq = (uint32_t)x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
+                    a.recs[(int64_t)r * a.cap_rec + nr] = rec;
+                }
+                nr++; nh += (uint32_t)x2;
+                start += len;
+            } else start++;
+            searching = false;
+        }
+    }
+    if (q == 0 && st_steps) {
+        atomicAdd(&a.stats->ext_steps, st_steps);
+        atomicAdd(&a.stats->ext_blocks, st_blocks);
+    }
+}
+
+void launch_search(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
+{
+    if (a.n_reads <= 0) return;
+    int want = (a.n_reads + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
+    int grid = want < 148 * 16 ? want : 148 * 16; // 16 CTAs of 128 threads fill an SM's 2048 thread slots
+    k_search<<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prefix sums (plumbing): seed_off = exclusive scan of nhits over n_reads+1 entries (nhits[n_reads] == 0)
+// ---------------------------------------------------------------------------------------------------
+struct U32ToI64 { __host__ __device__ int64_t operator()(const uint32_t &v) const { return (int64_t)v; } };
+
+size_t scan_tmp_bytes(int n)
+{
+    size_t bytes = 0;
+    cub::TransformInputIterator<int64_t, U32ToI64, const uint32_t *> it((const uint32_t *)nullptr, U32ToI64());
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (int64_t *)nullptr, n + 1);
+    return bytes;
+}
+
+void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    cub::TransformInputIterator<int64_t, U32ToI64, const uint32_t *> it(in, U32ToI64());
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, out, n + 1, st);
+}
+
+void launch_scan_hits(const SeedLaunch &a, void *tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    launch_scan_u32_to_i64(a.nhits, a.seed_off, a.n_reads, tmp, tmp_bytes, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel 2a: expand the recorded SA intervals into one slot per hit (slot = SA index still to resolve)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_expand(SeedLaunch a)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; r < a.n_reads; r += gridDim.x * blockDim.x) {
+        int64_t o = a.seed_off[r];
+        int nr = min((int)a.nrec[r], a.cap_rec);
+        for (int i = 0; i < nr; i++) {
+            SearchRec rec = a.recs[(int64_t)r * a.cap_rec + i];
+            uint32_t m = (uint32_t)rec.start << 16 | rec.len;
+            for (uint32_t j = 0; j < rec.freq; j++, o++) { a.keys[o] = rec.x0 + j; a.meta[o] = m; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel 2b: SA locate — bwt_sa / bwt_invPsi (bwt_search.cpp:119-137), one group per hit
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEARCH_THREADS)
+k_locate(DevIndex ix, SeedLaunch a, int64_t total)
+{
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const unsigned gmask = 0xFu << (lane & ~3);
+    const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_CTA;
+    unsigned long long st_lf = 0, st_hits = 0;
+    for (int64_t s = (int64_t)blockIdx.x * GROUPS_PER_CTA + (threadIdx.x >> 2); s < total; s += ngroups) {
+        uint64_t k = a.keys[s];
+        uint32_t steps = 0;
+        while (k & ix.sa_mask) {
+            steps++;
+            if (k == ix.primary) { k = 0; continue; }
+            uint64_t kk = k - (k > ix.primary);
+            ulonglong2 v = load_quarter(ix, kk, q);
+            int o = (int)(kk & 127);
+            int c_here = (int)((v.y >> (62 - 2 * (o & 31))) & 3);
+            int c = __shfl_sync(gmask, c_here, o >> 5, 4);
+            uint64_t nxt = ix.L2[q] + finish_rank(v, kk, q, gmask);
+            k = __shfl_sync(gmask, nxt, c, 4);
+        }
+        uint64_t g = (uint64_t)steps + __ldg(ix.sa + (k >> ix.sa_shift));
+        if (q == 0) {
+            uint32_t m = a.meta[s];
+            a.keys[s] = seed_key(g, m >> 16, m & 0xFFFF);
+        }
+        st_lf += steps; st_hits++;
+    }
+    if (q == 0 && st_hits) {
+        atomicAdd(&a.stats->lf_steps, st_lf);
+        atomicAdd(&a.stats->hits, st_hits);
+        atomicAdd(&a.stats->seeds, st_hits);
+    }
+}
+
+void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, int64_t total, cudaStream_t st)
+{
+    if (a.n_reads <= 0 || total <= 0) return;
+    int grid = (a.n_reads + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_expand<<<grid, 256, 0, st>>>(a);
+    int64_t want = (total + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
+    int g2 = (int)(want < 148 * 16 ? want : 148 * 16);
+    k_locate<<<g2, SEARCH_THREADS, 0, st>>>(ix, a, total);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel 3: per-read sort by (gPos,rPos) + clustering (GenerateAlignmentCandidate)
+// ---------------------------------------------------------------------------------------------------
+// ChrLocMap.lower_bound(g)->first : last coordinate of the sequence that contains g
+__device__ __forceinline__ int64_t chr_end_of(const DevIndex &ix, int64_t g)
+{
+    int lo = 0, hi = ix.n_ends;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ix.chr_ends[mid] < g) lo = mid + 1; else hi = mid;
+    }
+    return ix.chr_ends[min(lo, ix.n_ends - 1)];
+}
+
+// the chaining test of AlignmentCandidates.cpp:264-265 between consecutive sorted seeds j -> k
+__device__ __forceinline__ bool chains(const DevIndex &ix, int64_t gj, int rj, int64_t gk, int rk, int max_gaps, int max_intron)
+{
+    int64_t d = (gk - rk) - (gj - rj);
+    if (d < 0) d = -d;
+    if (d < max_gaps) return true;
+    return d < max_intron && gk < chr_end_of(ix, gj) && rk > rj;
+}
+
+__device__ __forceinline__ int cand_threshold(int rlen) { return (int)((double)rlen * 0.3); } // AlignmentCandidates.cpp:251
+
+__global__ void __launch_bounds__(256)
+k_sort_cluster_warp(DevIndex ix, SeedLaunch a)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
+        int64_t off = a.seed_off[r];
+        int64_t n64 = a.seed_off[r + 1] - off;
+        if (n64 == 0) { if (lane == 0) a.ncand[r] = 0; continue; }
+        if (n64 > 32) {
+            if (lane == 0) { uint32_t i = atomicAdd(a.big_count, 1u); a.big_list[i] = (uint32_t)r; }
+            continue;
+        }
+        int n = (int)n64;
+        uint64_t key = lane < n ? a.keys[off + lane] : ~0ull;
+        // bitonic sort across the warp, ascending
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                uint64_t other = __shfl_xor_sync(FULL, key, j);
+                bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                key = keep_min ? (key < other ? key : other) : (key > other ? key : other);
+            }
+        }
+        bool valid = lane < n;
+        if (valid) a.keys[off + lane] = key;
+        int64_t g = key_gpos(key);
+        int rp = key_rpos(key), len = key_len(key);
+        int64_t pd = g - rp;
+        unsigned nonneg = __ballot_sync(FULL, valid && pd >= 0);
+        int first = nonneg ? __ffs(nonneg) - 1 : n;
+        int64_t gprev = __shfl_up_sync(FULL, g, 1);
+        int rprev = __shfl_up_sync(FULL, rp, 1);
+        bool in = valid && lane >= first;
+        bool chain = in && lane > first && chains(ix, gprev, rprev, g, rp, a.max_gaps, a.max_intron);
+        bool head = in && !chain;
+        int v = in ? len : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, v, d); if (lane >= d) v += t; }
+        unsigned heads = __ballot_sync(FULL, head);
+        unsigned higher = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+        int nh = higher ? __ffs(higher) - 1 : n;
+        int last = min(max(nh - 1, 0), 31);
+        int pend = __shfl_sync(FULL, v, last);
+        int pprev = __shfl_up_sync(FULL, v, 1);
+        if (lane == 0) pprev = 0;
+        int score = pend - pprev;
+        bool keep = head && score > cand_threshold(a.rlen[r]);
+        unsigned km = __ballot_sync(FULL, keep);
+        if (keep) {
+            int ci = __popc(km & ((1u << lane) - 1u));
+            a.cand_begin[off + ci] = lane;
+            a.cand_count[off + ci] = nh - lane;
+            a.cand_score[off + ci] = score;
+        }
+        if (lane == 0) a.ncand[r] = __popc(km);
+    }
+}
+
+constexpr int BIG_SM_CAP = 4096; // keys sorted in shared memory up to this many (padded to a power of two)
+
+__global__ void __launch_bounds__(256)
+k_sort_cluster_big(DevIndex ix, SeedLaunch a)
+{
+    __shared__ uint64_t sm[BIG_SM_CAP];
+    const int tid = threadIdx.x;
+    const uint32_t nbig = *a.big_count;
+    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+        int r = (int)a.big_list[b];
+        int64_t off = a.seed_off[r];
+        int64_t n = a.seed_off[r + 1] - off;
+        int64_t N = 64;
+        while (N < n) N <<= 1;
+        uint64_t *buf = sm;
+        if (N > BIG_SM_CAP) {
+            if ((size_t)N > a.big_scratch_per_cta) { if (tid == 0) a.ncand[r] = 0xFFFFFFFFu; continue; } // cannot happen: bound = cap_rec*max_dup
+            buf = a.big_scratch + (size_t)blockIdx.x * a.big_scratch_per_cta;
+        }
+        for (int64_t i = tid; i < N; i += blockDim.x) buf[i] = i < n ? a.keys[off + i] : ~0ull;
+        __syncthreads();
+        for (int64_t k = 2; k <= N; k <<= 1)
+            for (int64_t j = k >> 1; j > 0; j >>= 1) {
+                for (int64_t i = tid; i < N; i += blockDim.x) {
+                    int64_t p = i ^ j;
+                    if (p > i) {
+                        uint64_t x = buf[i], y = buf[p];
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) { buf[i] = y; buf[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int64_t i = tid; i < n; i += blockDim.x) a.keys[off + i] = buf[i];
+        __syncthreads();
+        if (tid == 0) { // the greedy scan itself, sequential: big reads are rare outside config 5
+            int thr = cand_threshold(a.rlen[r]);
+            int64_t i = 0;
+            uint32_t nc = 0;
+            while (i < n && key_gpos(buf[i]) - key_rpos(buf[i]) < 0) i++;
+            while (i < n) {
+                int score = key_len(buf[i]);
+                int64_t k = i + 1;
+                for (; k < n; k++) {
+                    if (!chains(ix, key_gpos(buf[k - 1]), key_rpos(buf[k - 1]), key_gpos(buf[k]), key_rpos(buf[k]),
+                                a.max_gaps, a.max_intron)) break;
+                    score += key_len(buf[k]);
+                }
+                if (score > thr) {
+                    a.cand_begin[off + nc] = (int32_t)i;
+                    a.cand_count[off + nc] = (int32_t)(k - i);
+                    a.cand_score[off + nc] = score;
+                    nc++;
+                }
+                i = k;
+            }
+            a.ncand[r] = nc;
+        }
+        __syncthreads();
+    }
+}
+
+void launch_sort_cluster(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
+{
+    if (a.n_reads <= 0) return;
+    cudaMemsetAsync(a.big_count, 0, sizeof(uint32_t), st);
+    int64_t want = ((int64_t)a.n_reads * 32 + 255) / 256;
+    int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    k_sort_cluster_warp<<<grid, 256, 0, st>>>(ix, a);
+    k_sort_cluster_big<<<148, 256, 0, st>>>(ix, a);
+}
+
+} // namespace dartgpu

@@ -1,0 +1,209 @@
+/* dartgpu.h — the C-ABI boundary of the B200 mapping hot path (libdartgpu.so).
+ *
+ * The reference has no plugin/FFI interface for this path: the boundary is the set of C++ free
+ * functions declared in /root/reference/src/structure.h:192-233 and called from ReadMapping()
+ * (/root/reference/src/Mapping.cpp:600-639).  Each entry point below replaces one of those call sites,
+ * batched over many reads (the reference's own chunk is <=4000 reads, src/GetData.cpp:176 — far too
+ * small for a B200, so the caller aggregates chunks).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns DARTGPU_OK (0) or a negative DARTGPU_ERR_* code; dartgpu_last_error(ctx)
+ *     has the text.  There is NO CPU fallback: without a usable CUDA device every call fails.
+ *   - one context per (host thread, GPU).  Contexts on the same device share nothing but the driver.
+ *   - result buffers are owned by the context (pinned host memory) and stay valid until the next call
+ *     on the same context.
+ *   - genome coordinates are the reference's: [0,G) forward strand, [G,2G) reverse complement
+ *     (src/bwt_index.cpp:234, src/AlignmentCandidates.cpp:88-108); int64 everywhere.
+ *   - read bases arrive as the ASCII the reference keeps in ReadItem_t.seq (src/structure.h:149-164);
+ *     mate 2 already reverse-complemented as GetNextChunk leaves it (src/GetData.cpp:157-168).
+ */
+#ifndef DARTGPU_H
+#define DARTGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DARTGPU_OK                 0
+#define DARTGPU_ERR_NO_DEVICE     -1   /* no CUDA device / driver: the product path refuses to run */
+#define DARTGPU_ERR_CUDA          -2   /* a CUDA call or kernel failed */
+#define DARTGPU_ERR_INDEX         -3   /* index files missing or inconsistent */
+#define DARTGPU_ERR_ARG           -4   /* bad argument (NULL, negative size, ...) */
+#define DARTGPU_ERR_READ_TOO_LONG -5   /* a read exceeds DARTGPU_MAX_RLEN */
+#define DARTGPU_ERR_NOMEM         -6
+#define DARTGPU_MAX_RLEN        1024   /* the reference's .gz reader caps lines at 1023 chars (src/GetData.cpp:186) */
+
+typedef struct dartgpu_ctx dartgpu_ctx;
+
+/* The hot-path globals of the reference (src/structure.h:182-185) as one POD; defaults = src/main.cpp:101-117. */
+typedef struct {
+    int32_t  max_gaps;      /* MaxGaps        = 5                                   */
+    int32_t  max_intron;    /* MaxIntronSize  = 500000 (flag parser clamps >=100000) */
+    int32_t  min_intron;    /* MinIntronSize  = 5                                   */
+    int32_t  max_mismatch;  /* MaxMismatch    = 0  (-mis)             */
+    uint32_t max_dup;       /* MaxDupNum      = 100 (-max_dup, clamped 100..10000)  */
+    int32_t  multi_hit;     /* bMultiHit (-m)                                        */
+    int32_t  pair_end;      /* bPairEnd: reads 2i,2i+1 are mates                      */
+    int32_t  all_sj;        /* bFindAllJunction (-all_sj)                             */
+    int32_t  unique;        /* bUnique (-unique)                                      */
+    int32_t  host_threads;  /* worker threads for the host-side orchestration; 0 = all cores */
+} dartgpu_params;
+
+void dartgpu_default_params(dartgpu_params *p);
+
+/* The loaded index exactly as the reference holds it after bwa_idx_load()+RestoreReferenceInfo()
+ * (bwt_t / bntseq_t, src/structure.h:29-69): what a patched Mapping.cpp passes once at start-up. */
+typedef struct {
+    uint64_t        primary;      /* bwt_t.primary                                  */
+    uint64_t        L2[5];        /* bwt_t.L2                                       */
+    uint64_t        seq_len;      /* bwt_t.seq_len (= 2G)                           */
+    uint64_t        bwt_size;     /* bwt_t.bwt_size, in 32-bit words                */
+    const uint32_t *bwt;          /* bwt_t.bwt: 64-byte blocks, 4 x u64 Occ + 8 x u32 symbols */
+    uint64_t        sa_intv;      /* bwt_t.sa_intv (32)                             */
+    uint64_t        n_sa;         /* bwt_t.n_sa                                     */
+    const uint64_t *sa;           /* bwt_t.sa, sa[0] = (uint64_t)-1                 */
+    int64_t         l_pac;        /* bntseq_t.l_pac = G                             */
+    const uint8_t  *pac;          /* bwaidx_t.pac: 2-bit, forward strand, l_pac/4+1 bytes */
+    int32_t         n_seqs;       /* bntseq_t.n_seqs                                */
+    const int64_t  *seq_len_arr;  /* bntann1_t.len for each sequence                */
+    const char *const *seq_names; /* bntann1_t.name                                 */
+} dartgpu_index_view;
+
+/* Replaces: the once-per-run index hand-over (src/main.cpp:220-223).  The tables are re-laid-out on the GPU
+ * (128-bit-interleaved Occ blocks, 2-bit reference over both strands) and stay resident in HBM. */
+int  dartgpu_create(dartgpu_ctx **out, int device, const dartgpu_index_view *idx, const dartgpu_params *p);
+/* Convenience: read <prefix>.bwt/.sa/.pac/.ann written by bwt_index / `dart index` / bwa index
+ * (formats: src/bwt_index.cpp:15-35, :37-89, :102-121) and call dartgpu_create. */
+int  dartgpu_create_from_files(dartgpu_ctx **out, int device, const char *prefix, const dartgpu_params *p);
+void dartgpu_destroy(dartgpu_ctx *ctx);
+int  dartgpu_set_params(dartgpu_ctx *ctx, const dartgpu_params *p);
+const char *dartgpu_last_error(const dartgpu_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
+int64_t dartgpu_genome_size(const dartgpu_ctx *ctx);
+int  dartgpu_num_sequences(const dartgpu_ctx *ctx);
+const char *dartgpu_sequence_name(const dartgpu_ctx *ctx, int i);
+int64_t dartgpu_sequence_length(const dartgpu_ctx *ctx, int i);
+/* Work on `stream` (a cudaStream_t) instead of the context's own stream, e.g. the caller's current stream. */
+int  dartgpu_set_stream(dartgpu_ctx *ctx, void *cuda_stream);
+
+/* ---- a batch of reads ------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t        n_reads;
+    const char    *bases;     /* concatenated ReadItem_t.seq, no terminators                     */
+    const int64_t *offsets;   /* n_reads+1 offsets into bases; rlen = offsets[i+1]-offsets[i]     */
+} dartgpu_reads;
+
+/* ---- stage 1: IdentifySeedPairs + GenerateAlignmentCandidate ------------------------------------------
+ * Replaces, for every read of the batch: IdentifySeedPairs(rlen, EncodeSeq) (src/AlignmentCandidates.cpp:181-215,
+ * with BWT_Search/bwt_sa, src/bwt_search.cpp:127-182) and GenerateAlignmentCandidate(rlen, seeds)
+ * (src/AlignmentCandidates.cpp:241-288).
+ * Seeds of read i are seeds[seed_off[i] .. seed_off[i+1]), sorted by (gPos,rPos) as the reference sorts them.
+ * Candidate c of read i covers seeds seed_off[i]+cand_begin[k] .. +cand_count[k], k = cand_off[i]+c; its
+ * PosDiff is max(seed.gPos-seed.rPos, 0) of its first seed. */
+typedef struct {
+    const int64_t *seed_off;    /* n_reads+1 */
+    const int64_t *seed_gpos;   /* SeedPair_t.gPos */
+    const int32_t *seed_rpos;   /* SeedPair_t.rPos */
+    const int32_t *seed_len;    /* SeedPair_t.rLen = gLen */
+    const int64_t *cand_off;    /* n_reads+1 */
+    const int32_t *cand_begin;  /* first seed, relative to the read's first seed */
+    const int32_t *cand_count;  /* number of seeds */
+    const int32_t *cand_score;  /* AlignmentCandidate_t.Score */
+} dartgpu_seeds;
+
+int dartgpu_seed_and_cluster(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_seeds *out);
+
+/* ---- stage 2: 8-mer re-seeding inside a (read gap, genome window) --------------------------------------
+ * Replaces GenerateLongestSimplePairsFromFragmentPair(len1, frag1, len2, frag2) (src/KmerAnalysis.cpp:134-166)
+ * as called by ReseedingWithSpecificRegion (src/AlignmentCandidates.cpp:596-624): frag1 = read bases
+ * [frag_off, frag_off+frag_len) of `bases`, frag2 = RefSequence[gpos, gpos+glen).
+ * Result: SeedPair_t {rPos, gPos, rLen} in fragment-local coordinates; rLen = 0 when nothing was found. */
+typedef struct { int64_t frag_off; int32_t frag_len; int32_t glen; int64_t gpos; } dartgpu_kmer_job;
+typedef struct { int32_t rpos; int32_t gpos; int32_t len; } dartgpu_kmer_hit;
+
+int dartgpu_kmer_reseed(dartgpu_ctx *ctx, const char *bases, int64_t n_bases,
+                        const dartgpu_kmer_job *jobs, int32_t n_jobs, const dartgpu_kmer_hit **out);
+
+/* ---- stage 3: Needleman-Wunsch gap fill ----------------------------------------------------------------
+ * Replaces nw_alignment(m, s1, n, s2) (src/nw_alignment.cpp:18-82) at its call sites
+ * (src/AlignmentCandidates.cpp:395, :420; src/tools.cpp:156, :220, :268): s1 = read bases
+ * [frag_off, frag_off+m) of `bases`, s2 = RefSequence[gpos, gpos+n).
+ * Result per job: the alignment columns left to right, one byte each:
+ *   0 = s1 and s2 both advance, 1 = '-' inserted into s1 (s2 advances), 2 = '-' inserted into s2.
+ * Columns of job j are ops[op_off[j] .. op_off[j+1]). */
+typedef struct { int64_t frag_off; int32_t m; int32_t n; int64_t gpos; } dartgpu_nw_job;
+typedef struct { const int64_t *op_off; const uint8_t *ops; } dartgpu_nw_result;
+
+int dartgpu_nw_align(dartgpu_ctx *ctx, const char *bases, int64_t n_bases,
+                     const dartgpu_nw_job *jobs, int32_t n_jobs, dartgpu_nw_result *out);
+
+/* ---- the whole per-read path -----------------------------------------------------------------------------
+ * Replaces the body of the per-read loop of ReadMapping() (src/Mapping.cpp:600-639): seeds, candidates, mate
+ * pairing of candidates, GenMappingReport (src/AlignmentCandidates.cpp:1079-1207), CheckPairedFinalAlignments,
+ * Set*AlignmentFlag, EvaluateMAPQ and the junctions UpdateLocalSJMap would record.  The caller keeps its own
+ * reader and its own OutputPaired/SingledAlignments + OutputSpliceJunctions.
+ * With params.pair_end the batch holds mates at 2i, 2i+1 (n_reads even). */
+typedef struct {            /* = the report fields of ReadItem_t (src/structure.h:156-163) */
+    int32_t mapq, score, sub_score, mis_num;
+    int32_t n_reports;      /* CanNum */
+    int32_t best;           /* iBestAlnCanIdx */
+    int64_t report_off;     /* first AlignmentReport of this read in reports[] */
+} dartgpu_read_result;
+
+typedef struct {            /* = AlignmentReport_t + Coordinate_t (src/structure.h:117-141) */
+    int32_t aln_score;      /* AlnScore */
+    int32_t sj_type;        /* SJtype, -1 = none */
+    int32_t flag;           /* iFrag (SAM FLAG); meaningful where the reference assigns it */
+    int32_t paired_idx;     /* PairedAlnCanIdx */
+    int32_t dir;            /* coor.bDir (1 forward); valid when aln_score > 0 */
+    int32_t chr_idx;        /* coor.ChromosomeIdx */
+    int64_t pos;            /* coor.gPos (1-based on the chromosome) */
+    int64_t cigar_off;      /* coor.CIGAR = cigars[cigar_off .. cigar_off+cigar_len) */
+    int32_t cigar_len;
+    int32_t reserved;
+} dartgpu_report;
+
+typedef struct {            /* one UpdateLocalSJMap increment (src/Mapping.cpp:532-565) */
+    int64_t g1, g2;         /* absolute coordinates as the map keys them */
+    int32_t type;           /* SJtype of the alignment */
+    int32_t read;           /* read index in the batch */
+} dartgpu_junction;
+
+typedef struct {
+    const dartgpu_read_result *reads;   int32_t n_reads;
+    const dartgpu_report      *reports; int64_t n_reports;
+    const char                *cigars;  int64_t n_cigar_bytes;
+    const dartgpu_junction    *junctions; int64_t n_junctions;
+} dartgpu_map_result;
+
+int dartgpu_map_reads(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_map_result *out);
+
+/* ---- measurement ------------------------------------------------------------------------------------------
+ * Device time (CUDA events on the context's stream) and algorithmic work of the kernels launched by the LAST
+ * call, for roofline reporting. */
+typedef struct {
+    double   ms_search, ms_locate, ms_sort_cluster, ms_kmer, ms_nw, ms_h2d, ms_d2h, ms_total_device;
+    double   ms_host;                 /* host-side orchestration inside the call */
+    uint64_t kernel_launches;
+    uint64_t ext_steps, ext_blocks;   /* forward-extension steps and the 64-byte Occ blocks they touched */
+    uint64_t lf_steps, hits, seeds;   /* LF-mapping steps (one block each), SA reads, seeds written */
+    uint64_t read_bases;
+    uint64_t nw_jobs, nw_cells;
+    uint64_t kmer_jobs, kmer_window_bases, kmer_read_bases;
+    uint64_t h2d_bytes, d2h_bytes;
+} dartgpu_stats;
+
+int dartgpu_get_stats(const dartgpu_ctx *ctx, dartgpu_stats *out);
+
+/* Device-resident variant of stage 1 for kernel-only timing: upload once, run the seeding kernels many times
+ * without any host<->device copy in between (bench.py `value`). */
+int dartgpu_upload_reads(dartgpu_ctx *ctx, const dartgpu_reads *reads);
+int dartgpu_seed_and_cluster_resident(dartgpu_ctx *ctx);   /* results stay on the device */
+/* dartgpu_map_reads over the batch previously uploaded with dartgpu_upload_reads (same `reads`): no read H2D. */
+int dartgpu_map_reads_resident(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_map_result *out);
+int dartgpu_synchronize(dartgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DARTGPU_H */

@@ -1,0 +1,47 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol include/dartgpu.h declares,
+and refuses to run (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import GOLDEN, ROOT, have_gpu
+from dart_b200 import capi
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.load_library()
+    header = open(os.path.join(ROOT, "include", "dartgpu.h")).read()
+    declared = set(re.findall(r"\b(dartgpu_[a-z_]+)\s*\(", header))
+    assert declared == set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_structs_match_the_header_layout():
+    assert C.sizeof(capi.Params) == 40
+    assert capi.KMER_JOB.itemsize == 24 and capi.NW_JOB.itemsize == 24 and capi.KMER_HIT.itemsize == 12
+    assert capi.READ_RESULT.itemsize == 32 and capi.REPORT.itemsize == 48 and capi.JUNCTION.itemsize == 24
+
+
+def test_default_params_are_the_reference_defaults():
+    L = capi.load_library()
+    p = capi.Params()
+    L.dartgpu_default_params(C.byref(p))
+    # /root/reference/src/main.cpp:101-117
+    assert (p.max_gaps, p.max_intron, p.min_intron, p.max_mismatch, p.max_dup) == (5, 500000, 5, 0, 100)
+    assert (p.multi_hit, p.pair_end, p.all_sj, p.unique) == (0, 0, 0, 0)
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-device error path")
+def test_no_device_means_no_result():
+    with pytest.raises(capi.DartGpuError) as e:
+        capi.Mapper(os.path.join(GOLDEN, "idx"))
+    assert e.value.code == -1 and "no CPU fallback" in str(e.value)
+
+
+def test_missing_index_is_reported():
+    with pytest.raises(capi.DartGpuError) as e:
+        capi.Mapper("/nonexistent/prefix")
+    assert e.value.code == -3

@@ -1,0 +1,67 @@
+"""End-to-end parity: dart_b200_map (reader + SAM writer stand-in over libdartgpu.so) against the canonicalised
+reference binary (oracle/_ref/dart_canon -t 1) on scaled versions of all five BASELINE.json
+configs, with the flags each config names and with -mis 5. SAM records and junctions.tab must be
+byte-identical."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT, run_reference, workload
+
+pytestmark = pytest.mark.gpu
+TOOL = os.path.join(ROOT, "dart_b200", "dart_b200_map")
+
+
+def _records(path):
+    return [l for l in open(path) if not l.startswith("@")]
+
+
+def _headers(path):
+    return [l for l in open(path) if l.startswith("@")]
+
+
+def _run_gpu(w, extra=(), tag="gpu", more=()):
+    sam, junc = os.path.join(w["dir"], f"{tag}.sam"), os.path.join(w["dir"], f"{tag}.junc")
+    cmd = [TOOL, "-i", w["idx"], "-f", w["r1"]] + (["-f2", w["r2"]] if w["r2"] else [])
+    cmd += ["-o", sam, "-j", junc] + list(w["flags"]) + list(extra) + list(more)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return sam, junc
+
+
+def _compare(a, b, ja, jb):
+    ra, rb = _records(a), _records(b)
+    assert len(ra) == len(rb)
+    bad = [(x, y) for x, y in zip(ra, rb) if x != y]
+    assert not bad, f"{len(bad)} of {len(ra)} SAM records differ; first:\n{bad[0][0]}{bad[0][1]}"
+    assert _headers(a) == _headers(b)
+    assert open(ja).read() == open(jb).read()
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5"])
+@pytest.mark.parametrize("extra", [(), ("-mis", "5")], ids=["as-named", "mis5"])
+def test_sam_and_junctions_identical(name, extra):
+    w = workload(name)
+    if name == "c4" and extra:
+        pytest.skip("config 4 already names -mis 10")
+    tag = "mis5" if extra else "named"
+    rs, rj = run_reference(w, "dart_canon", 1, extra, tag="ref_" + tag)
+    gs, gj = _run_gpu(w, extra, tag="gpu_" + tag)
+    _compare(gs, rs, gj, rj)
+
+
+def test_result_is_independent_of_batching_and_host_threads():
+    w = workload("c3")
+    rs, rj = run_reference(w, "dart_canon", 1, ("-mis", "5"), tag="ref_mis5")
+    gs, gj = _run_gpu(w, ("-mis", "5"), tag="gpu_small_batches", more=("-batch", "500", "-t", "3"))
+    _compare(gs, rs, gj, rj)
+
+
+def test_golden_sam():
+    """The committed golden SAM (generated in the build container from the reference) — no oracle/_ref needed."""
+    w = dict(dir=os.environ.get("DART_TEST_DIR", "/tmp/dart_b200_tests"), idx=GOLDEN + "/idx", flags=["-mis", "5"])
+    os.makedirs(w["dir"], exist_ok=True)
+    for tag, r1, r2 in (("se", "se.fq", None), ("pe", "pe1.fq", "pe2.fq")):
+        w.update(r1=os.path.join(GOLDEN, r1), r2=os.path.join(GOLDEN, r2) if r2 else None)
+        gs, gj = _run_gpu(w, tag="golden_" + tag)
+        _compare(gs, os.path.join(GOLDEN, tag + ".sam"), gj, os.path.join(GOLDEN, tag + ".junc"))
