@@ -93,8 +93,18 @@ def run_reference(w, binary="dart_canon", threads=1, extra=(), tag="ref"):
     if w["r2"]:
         cmd += ["-f2", w["r2"]]
     cmd += ["-t", str(threads), "-o", sam, "-j", junc] + list(w["flags"]) + list(extra)
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, env=canonical_env())
     return sam, junc
+
+
+def canonical_env():
+    """The canonical oracle = the reference with every uninitialised object zero-filled: the stack
+    object `ReadItem_t read` by the build flags of oracle/Makefile (dart_canon), heap objects (`new AlignmentReport_t[]`,
+    whose iFrag / coor.bDir the reference prints without ever assigning them for secondary -m reports) by glibc's
+    MALLOC_PERTURB_=255, which fills fresh allocations with ~0xFF = 0x00."""
+    env = dict(os.environ)
+    env["MALLOC_PERTURB_"] = "255"
+    return env
 
 
 def have_gpu():

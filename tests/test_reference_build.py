@@ -3,7 +3,7 @@ agreement of the in-process taps with the stock binary."""
 import os
 import subprocess
 
-from conftest import GOLDEN, need_ref, read_fastq_seqs
+from conftest import GOLDEN, canonical_env, need_ref, read_fastq_seqs
 from oracle import pyoracle as po
 
 
@@ -17,7 +17,8 @@ def test_canon_matches_stock_on_mapped_reads_and_golden(tmp_path):
     for b in ("dart_ref", "dart_canon"):
         sam, junc = str(tmp_path / f"{b}.sam"), str(tmp_path / f"{b}.junc")
         subprocess.run([os.path.join(po.REF_DIR, b), "-i", GOLDEN + "/idx", "-f", GOLDEN + "/pe1.fq", "-f2", GOLDEN + "/pe2.fq",
-                        "-t", "1", "-mis", "5", "-o", sam, "-j", junc], check=True, stdout=subprocess.DEVNULL)
+                        "-t", "1", "-mis", "5", "-o", sam, "-j", junc], check=True, stdout=subprocess.DEVNULL,
+                       env=canonical_env() if b == "dart_canon" else None)
         out[b] = (_records(sam), open(junc).read())
     assert out["dart_canon"][0] == _records(GOLDEN + "/pe.sam")      # the committed golden SAM is reproducible
     assert out["dart_canon"][1] == open(GOLDEN + "/pe.junc").read()

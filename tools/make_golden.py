@@ -43,10 +43,11 @@ def main():
     synth.write_fastq(os.path.join(OUT, "pe1.fq"), m1, 1)
     synth.write_fastq(os.path.join(OUT, "pe2.fq"), m2, 2)
     ref = os.path.join(ROOT, "oracle", "_ref", "dart_canon")
+    env = dict(os.environ, MALLOC_PERTURB_="255")   # zero-filled heap: see tests/conftest.py canonical_env()
     subprocess.run([ref, "-i", OUT + "/idx", "-f", OUT + "/se.fq", "-t", "1", "-mis", "5", "-o", OUT + "/se.sam",
-                    "-j", OUT + "/se.junc"], check=True, stdout=subprocess.DEVNULL)
+                    "-j", OUT + "/se.junc"], check=True, stdout=subprocess.DEVNULL, env=env)
     subprocess.run([ref, "-i", OUT + "/idx", "-f", OUT + "/pe1.fq", "-f2", OUT + "/pe2.fq", "-t", "1", "-mis", "5",
-                    "-o", OUT + "/pe.sam", "-j", OUT + "/pe.junc"], check=True, stdout=subprocess.DEVNULL)
+                    "-o", OUT + "/pe.sam", "-j", OUT + "/pe.junc"], check=True, stdout=subprocess.DEVNULL, env=env)
 
     R = po.Reference(OUT + "/idx")
     R.set_params(max_mismatch=5)
