@@ -53,7 +53,7 @@ class _MapResult(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = ([(n, C.c_double) for n in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_h2d",
-                                           "ms_d2h", "ms_total_device", "ms_host")] +
+                                           "ms_d2h", "ms_total_device", "ms_host", "ms_report")] +
                 [(n, C.c_uint64) for n in ("kernel_launches", "ext_steps", "ext_blocks", "lf_steps", "hits", "seeds",
                                            "read_bases", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases",
                                            "kmer_read_bases", "h2d_bytes", "d2h_bytes")])

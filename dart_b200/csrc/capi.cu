@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <new>
@@ -19,7 +20,8 @@ static uint8_t *make_code_table()
 {
     static uint8_t t[256];
     for (int i = 0; i < 256; i++) t[i] = CODE_OTHER;
-    t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+    t['A'] = 0; t['C'] = 1; t['G'] = 2; t['T'] = 3;
+    t['a'] = 8; t['c'] = 9; t['g'] = 10; t['t'] = 11;   // same base codes, bit 3 = lower case (raw-character compares differ)
     t['N'] = CODE_N; // only the upper-case literal breaks an 8-mer (/root/reference/src/KmerAnalysis.cpp:44)
     return t;
 }
@@ -483,6 +485,7 @@ void dartgpu_destroy(dartgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->dpipe) free_device_pipe(c->dpipe);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -576,7 +579,7 @@ int dartgpu_nw_align(dartgpu_ctx *c, const char *bases, int64_t n_bases, const d
             const dartgpu_nw_job &j = jobs[i];
             if (j.frag_off < 0 || j.m < 0 || j.frag_off + j.m > n_bases || j.n < 0 || j.gpos < 0 || j.gpos + j.n > 2 * c->G)
                 throw std::make_pair(DARTGPU_ERR_ARG, std::string("NW job out of range"));
-            c->h_njobs.p[i] = NwJobDev{j.frag_off, j.gpos, 0, 0, j.m, j.n};
+            c->h_njobs.p[i] = NwJobDev{j.frag_off, j.gpos, 0, 0, 0, j.m, j.n};
         }
         run_nw(c, dcodes, c->h_njobs.p, n_jobs);
         out->op_off = c->o_op_off.data();
@@ -592,11 +595,9 @@ int dartgpu_map_reads(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_re
         Timer t;
         stats_begin(c);
         upload_reads(c, reads);
-        run_seeding(c, true);
-        double dev_before = c->stats.ms_kmer + c->stats.ms_nw;
-        (void)dev_before;
-        run_pipeline(c, reads, out);
-        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_h2d;
+        if (getenv("DARTGPU_HOST_PIPELINE")) { run_seeding(c, true); run_pipeline(c, reads, out); }
+        else { run_seeding(c, false); run_pipeline_device(c, out); }
+        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_h2d + c->stats.ms_report;
         c->stats.ms_host = t.ms();
     });
 }
@@ -611,9 +612,9 @@ int dartgpu_map_reads_resident(dartgpu_ctx *c, const dartgpu_reads *reads, dartg
         uint64_t rb = c->stats.read_bases;
         stats_begin(c);
         c->stats.read_bases = rb;
-        run_seeding(c, true);
-        run_pipeline(c, reads, out);
-        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw;
+        if (getenv("DARTGPU_HOST_PIPELINE")) { run_seeding(c, true); run_pipeline(c, reads, out); }
+        else { run_seeding(c, false); run_pipeline_device(c, out); }
+        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_report;
         c->stats.ms_host = t.ms();
     });
 }

@@ -81,6 +81,9 @@ struct dartgpu_ctx {
     std::vector<char> o_cigars;
     std::vector<dartgpu_junction> o_junctions;
 
+    // ---- device orchestration buffers (report_kernels.cu) ----
+    void *dpipe = nullptr;
+
     // ---- measurement ----
     dartgpu_stats stats{};
     cudaEvent_t ev[16] = {};
@@ -99,7 +102,9 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
 // NW jobs (op_off / flag_off are filled here). Results: c->o_op_off / c->o_ops (compacted, left-to-right columns).
 void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs);
 // the whole per-read path over the uploaded batch
-void run_pipeline(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out);
+void run_pipeline(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out);   // host orchestration (A/B only)
+void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out);                              // device orchestration
+void free_device_pipe(void *p);
 
 inline int host_ref_code(const dartgpu_ctx *c, int64_t p)
 {

@@ -45,8 +45,9 @@ __host__ __device__ inline int64_t key_gpos(uint64_t k) { return (int64_t)(k >> 
 __host__ __device__ inline int key_rpos(uint64_t k) { return (int)((k >> 15) & 0xFFFF); }
 __host__ __device__ inline int key_len(uint64_t k) { return (int)(k & 0x7FFF); }
 
-// device read encoding (one byte per base): 0..3 = A,C,G,T (either case), 4 = any other symbol,
-// 5 = a literal 'N' (the only symbol that breaks an 8-mer, /root/reference/src/KmerAnalysis.cpp:44)
+// device read encoding (one byte per base): 0..3 = A,C,G,T, 8..11 = a,c,g,t (bit 3 = lower case: the reference compares
+// raw characters in places), 4 = any other symbol, 5 = a literal 'N' (the only symbol that breaks an 8-mer,
+// /root/reference/src/KmerAnalysis.cpp:44).  Bit 2 set <=> not ACGT; (code & 3) is the base otherwise.
 enum { CODE_OTHER = 4, CODE_N = 5 };
 
 struct DevStats {            // device-side work counters (see dartgpu_stats)
@@ -113,7 +114,7 @@ void launch_sort_cluster(const DevIndex &ix, const SeedLaunch &a, cudaStream_t s
 void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 
 // nw_kernel.cu
-struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int32_t m, n; };
+struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int64_t aux_off; int32_t m, n; };
 void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,
                uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, cudaStream_t st);
 int nw_grid_warps();

@@ -24,6 +24,9 @@ namespace dartgpu {
 constexpr unsigned FULLK = 0xffffffffu;
 constexpr int KMER_THREADS = 128;
 
+// nst_nt4_table value of a device read code (0..3 ACGT, 8..11 acgt, 4 other, 5 'N')
+__device__ __forceinline__ uint32_t nt4(uint8_t c) { return (c & 4) ? 4u : (uint32_t)(c & 3); }
+
 __device__ __forceinline__ uint32_t genome_kmer(const DevIndex &ix, int64_t p)
 {
     const uint32_t *w = ix.ref2 + (p >> 4);
@@ -53,7 +56,7 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
             const uint8_t *s1 = codes + J.s1_off;
             // ---- 1. the read gap's 8-mer list ----
             bool bad = false;
-            for (int p = lane; p < L1; p += 32) bad |= s1[p] > 3;
+            for (int p = lane; p < L1; p += 32) bad |= (s1[p] & 4) != 0;
             bad = __any_sync(FULLK, bad);
             int nk = 0;
             if (!bad) {
@@ -61,7 +64,7 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                 for (int p = lane; p < nk; p += 32) {
                     uint32_t id = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) id = (id << 2) | s1[p + i];
+                    for (int i = 0; i < 8; i++) id = (id << 2) | (s1[p + i] & 3u);
                     tab[p] = id << 16 | (uint32_t)p;
                 }
             } else {
@@ -71,11 +74,11 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                     if (count == 8) {
                         head = tail - 8;
                         uint32_t wid = 0;
-                        for (int i = head; i < head + 8; i++) wid = (wid << 2) + min((int)s1[i], 4);
+                        for (int i = head; i < head + 8; i++) wid = (wid << 2) + nt4(s1[i]);
                         if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
                         for (head += 1; tail < L1; head++, tail++) {
                             if (s1[tail] != CODE_N) {
-                                wid = ((wid & 0x3FFFu) << 2) + min((int)s1[tail], 4);
+                                wid = ((wid & 0x3FFFu) << 2) + nt4(s1[tail]);
                                 if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
                             } else {
                                 count = 0; tail++;
@@ -83,7 +86,7 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                                 if (count != 8) break;
                                 head = tail - 8;
                                 wid = 0;
-                                for (int i = head; i < head + 8; i++) wid = (wid << 2) + min((int)s1[i], 4);
+                                for (int i = head; i < head + 8; i++) wid = (wid << 2) + nt4(s1[i]);
                                 if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
                             }
                         }

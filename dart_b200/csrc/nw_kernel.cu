@@ -47,7 +47,8 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
         for (int s0 = 0; s0 < m; s0 += 32) {
             const int i = s0 + lane + 1;              // my row (1-based)
             const bool rowok = i <= m;
-            const int a = rowok ? (int)codes[J.s1_off + i - 1] : 7;
+            int a = rowok ? (int)codes[J.s1_off + i - 1] : 7;
+            a = (a & 4) ? 7 : (a & 3);                // 8..11 are lower-case ACGT: same base for the table compare
             int Sl = -2 - i, Rl = NW_NEG;             // S[i][0], R[i][0]
             int Sd = (i == 1) ? 0 : -2 - (i - 1);     // S[i-1][0]
             int So = 0, To = 0, bo = 0;               // what I hand to the lane below

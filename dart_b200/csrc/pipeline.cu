@@ -513,8 +513,8 @@ void run_pipeline(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result
                     int rGaps = a.sv[i].rPos - (a.sv[i - 1].rPos + a.sv[i - 1].rLen);
                     int64_t s1 = r.code_off + a.sv[i - 1].rPos + a.sv[i - 1].rLen;
                     a.xjobs.push_back({i, (int)nj.size()});
-                    nj.push_back(NwJobDev{s1, a.sv[i - 1].gPos + a.sv[i - 1].gLen, 0, 0, rGaps, rGaps});
-                    nj.push_back(NwJobDev{s1, a.sv[i].gPos - rGaps, 0, 0, rGaps, rGaps});
+                    nj.push_back(NwJobDev{s1, a.sv[i - 1].gPos + a.sv[i - 1].gLen, 0, 0, 0, rGaps, rGaps});
+                    nj.push_back(NwJobDev{s1, a.sv[i].gPos - rGaps, 0, 0, 0, rGaps, rGaps});
                 }
             }
         }
@@ -597,7 +597,7 @@ void run_pipeline(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result
                 int nm;
                 if (simple_enough(c, r.seq, sp, &nm)) continue;
                 a.pjob[j] = (int)nj.size();
-                nj.push_back(NwJobDev{r.code_off + sp.rPos, sp.gPos, 0, 0, sp.rLen, sp.gLen});
+                nj.push_back(NwJobDev{r.code_off + sp.rPos, sp.gPos, 0, 0, 0, sp.rLen, sp.gLen});
             }
         }
     }

@@ -183,7 +183,8 @@ int dartgpu_map_reads(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_map_
  * call, for roofline reporting. */
 typedef struct {
     double   ms_search, ms_locate, ms_sort_cluster, ms_kmer, ms_nw, ms_h2d, ms_d2h, ms_total_device;
-    double   ms_host;                 /* host-side orchestration inside the call */
+    double   ms_host;                 /* wall time of the whole call on the host */
+    double   ms_report;               /* device orchestration kernels (candidate pairing, repair phases, records) */
     uint64_t kernel_launches;
     uint64_t ext_steps, ext_blocks;   /* forward-extension steps and the 64-byte Occ blocks they touched */
     uint64_t lf_steps, hits, seeds;   /* LF-mapping steps (one block each), SA reads, seeds written */

@@ -104,6 +104,7 @@ def canonical_env():
     MALLOC_PERTURB_=255, which fills fresh allocations with ~0xFF = 0x00."""
     env = dict(os.environ)
     env["MALLOC_PERTURB_"] = "255"
+    env["GLIBC_TUNABLES"] = "glibc.malloc.tcache_count=0"   # tcache hits bypass the perturbation
     return env
 
 

@@ -43,7 +43,7 @@ def main():
     synth.write_fastq(os.path.join(OUT, "pe1.fq"), m1, 1)
     synth.write_fastq(os.path.join(OUT, "pe2.fq"), m2, 2)
     ref = os.path.join(ROOT, "oracle", "_ref", "dart_canon")
-    env = dict(os.environ, MALLOC_PERTURB_="255")   # zero-filled heap: see tests/conftest.py canonical_env()
+    env = dict(os.environ, MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0")   # zero-filled heap: see tests/conftest.py canonical_env()
     subprocess.run([ref, "-i", OUT + "/idx", "-f", OUT + "/se.fq", "-t", "1", "-mis", "5", "-o", OUT + "/se.sam",
                     "-j", OUT + "/se.junc"], check=True, stdout=subprocess.DEVNULL, env=env)
     subprocess.run([ref, "-i", OUT + "/idx", "-f", OUT + "/pe1.fq", "-f2", OUT + "/pe2.fq", "-t", "1", "-mis", "5",
