@@ -76,46 +76,49 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
 {
     const int n = reads->n_reads;
     if (n < 0 || (n > 0 && (!reads->bases || !reads->offsets))) throw std::make_pair(DARTGPU_ERR_ARG, std::string("bad read batch"));
-    c->h_dev_off.reserve(n + 1);
-    c->h_rlen.reserve(n + 1);
-    int64_t off = 0;
-    int max_rlen = 0;
+    const int threads = c->prm.host_threads > 0 ? c->prm.host_threads : omp_get_max_threads();
+    int max_rlen = 0, bad = 0;
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(max : max_rlen) reduction(| : bad)
     for (int i = 0; i < n; i++) {
         int64_t rl = reads->offsets[i + 1] - reads->offsets[i];
-        if (rl < 0) throw std::make_pair(DARTGPU_ERR_ARG, std::string("read offsets are not monotone"));
-        if (rl > DARTGPU_MAX_RLEN) throw std::make_pair(DARTGPU_ERR_READ_TOO_LONG, std::string("a read is longer than DARTGPU_MAX_RLEN"));
-        c->h_dev_off.p[i] = off;
-        c->h_rlen.p[i] = (int32_t)rl;
-        max_rlen = std::max(max_rlen, (int)rl);
-        off += (rl + 15) & ~(int64_t)15;
+        if (rl < 0) bad |= 1;
+        else if (rl > DARTGPU_MAX_RLEN) bad |= 2;
+        else if ((int)rl > max_rlen) max_rlen = (int)rl;
     }
-    c->h_dev_off.p[n] = off;
-    c->h_codes.reserve(off + 16);
-    const int threads = c->prm.host_threads > 0 ? c->prm.host_threads : omp_get_max_threads();
+    if (bad & 1) throw std::make_pair(DARTGPU_ERR_ARG, std::string("read offsets are not monotone"));
+    if (bad & 2) throw std::make_pair(DARTGPU_ERR_READ_TOO_LONG, std::string("a read is longer than DARTGPU_MAX_RLEN"));
+    const int64_t first = n ? reads->offsets[0] : 0, n_bases = n ? reads->offsets[n] - first : 0;
+    c->h_raw.reserve(n_bases + 16); c->h_off.reserve(n + 2);
+    {   // stage the caller's (pageable) buffers into pinned memory with all cores
+        const int64_t chunk = 1 << 20, nchunks = (n_bases + chunk - 1) / chunk;
 #pragma omp parallel for schedule(static) num_threads(threads)
-    for (int i = 0; i < n; i++) {
-        const char *s = reads->bases + reads->offsets[i];
-        uint8_t *d = c->h_codes.p + c->h_dev_off.p[i];
-        int rl = c->h_rlen.p[i], padded = (rl + 15) & ~15;
-        for (int k = 0; k < rl; k++) d[k] = code_of((unsigned char)s[k]);
-        for (int k = rl; k < padded; k++) d[k] = CODE_OTHER;
+        for (int64_t k = 0; k < nchunks; k++)
+            memcpy(c->h_raw.p + k * chunk, reads->bases + first + k * chunk, (size_t)std::min(chunk, n_bases - k * chunk));
+        if (n) memcpy(c->h_off.p, reads->offsets, (size_t)(n + 1) * sizeof(int64_t));
     }
-    c->n_reads = n; c->max_rlen = max_rlen; c->n_code_bytes = off;
+    c->n_reads = n; c->max_rlen = max_rlen;
     c->cap_rec = std::max(1, (max_rlen + 15) / 16);
-    c->d_codes.reserve(off + 16);
-    c->d_dev_off.reserve(n + 1);
-    c->d_rlen.reserve(n + 1);
+    c->d_raw.reserve(n_bases + 16); c->d_off.reserve(n + 2); c->d_padded.reserve(n + 2);
+    c->d_dev_off.reserve(n + 2); c->d_rlen.reserve(n + 1);
+    const int64_t code_bytes = n_bases + 15ll * n + 16;      // upper bound of the padded layout
+    c->d_codes.reserve(code_bytes);
+    c->n_code_bytes = code_bytes;
     cudaStream_t st = c->stream;
     DG_CUDA(cudaEventRecord(c->ev[0], st));
     if (n) {
-        DG_CUDA(cudaMemcpyAsync(c->d_codes.p, c->h_codes.p, off, cudaMemcpyHostToDevice, st));
-        DG_CUDA(cudaMemcpyAsync(c->d_dev_off.p, c->h_dev_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        DG_CUDA(cudaMemcpyAsync(c->d_rlen.p, c->h_rlen.p, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemcpyAsync(c->d_raw.p, c->h_raw.p, n_bases, cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemcpyAsync(c->d_off.p, c->h_off.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        launch_read_layout(c->d_off.p, n, c->d_rlen.p, c->d_padded.p, st);
+        size_t tmp = scan_tmp_bytes(n);
+        c->d_scan_tmp.reserve(tmp + 256);
+        launch_scan_u32_to_i64(c->d_padded.p, c->d_dev_off.p, n, c->d_scan_tmp.p, tmp, st);
+        launch_encode_reads(c->d_raw.p, c->d_off.p, c->d_dev_off.p, n, c->d_codes.p, st);
+        DG_CUDA(cudaGetLastError());
+        c->stats.kernel_launches += 4;
     }
     DG_CUDA(cudaEventRecord(c->ev[1], st));
-    c->stats.h2d_bytes += off + (n + 1) * 8 + n * 4;
-    c->stats.read_bases = 0;
-    for (int i = 0; i < n; i++) c->stats.read_bases += c->h_rlen.p[i];
+    c->stats.h2d_bytes += n_bases + (uint64_t)(n + 1) * 8;
+    c->stats.read_bases = (uint64_t)n_bases;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -322,6 +325,9 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
         throw std::make_pair(DARTGPU_ERR_ARG, std::string("incomplete index view"));
     if (v->sa_intv == 0 || (v->sa_intv & (v->sa_intv - 1)))
         throw std::make_pair(DARTGPU_ERR_INDEX, std::string("SA sampling interval is not a power of two"));
+    for (int i = 0; i < 4; i++)
+        if (v->L2[i + 1] - v->L2[i] >= (1ull << 32))
+            throw std::make_pair(DARTGPU_ERR_INDEX, std::string("a symbol occurs 2^32 times or more: interval widths would not fit 32 bits"));
     if (v->seq_len != 2 * (uint64_t)v->l_pac)
         throw std::make_pair(DARTGPU_ERR_INDEX, std::string("index is not a forward+reverse-complement (FMD) index"));
     int ndev = 0;
@@ -595,8 +601,8 @@ int dartgpu_map_reads(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_re
         Timer t;
         stats_begin(c);
         upload_reads(c, reads);
-        if (getenv("DARTGPU_HOST_PIPELINE")) { run_seeding(c, true); run_pipeline(c, reads, out); }
-        else { run_seeding(c, false); run_pipeline_device(c, out); }
+        run_seeding(c, false);
+        run_pipeline_device(c, out);
         c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_h2d + c->stats.ms_report;
         c->stats.ms_host = t.ms();
     });
@@ -612,8 +618,8 @@ int dartgpu_map_reads_resident(dartgpu_ctx *c, const dartgpu_reads *reads, dartg
         uint64_t rb = c->stats.read_bases;
         stats_begin(c);
         c->stats.read_bases = rb;
-        if (getenv("DARTGPU_HOST_PIPELINE")) { run_seeding(c, true); run_pipeline(c, reads, out); }
-        else { run_seeding(c, false); run_pipeline_device(c, out); }
+        run_seeding(c, false);
+        run_pipeline_device(c, out);
         c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_report;
         c->stats.ms_host = t.ms();
     });

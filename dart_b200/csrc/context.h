@@ -31,9 +31,11 @@ struct dartgpu_ctx {
     // ---- read batch on the device ----
     int n_reads = 0, max_rlen = 0, cap_rec = 0;
     int64_t n_code_bytes = 0;
-    dartgpu::PinBuf<uint8_t> h_codes;
-    dartgpu::PinBuf<int64_t> h_dev_off;
-    dartgpu::PinBuf<int32_t> h_rlen;
+    dartgpu::PinBuf<uint8_t> h_raw;          // the caller's bases, staged for DMA
+    dartgpu::PinBuf<int64_t> h_off;
+    dartgpu::DevBuf<uint8_t> d_raw;
+    dartgpu::DevBuf<int64_t> d_off;
+    dartgpu::DevBuf<uint32_t> d_padded;
     dartgpu::DevBuf<uint8_t> d_codes;
     dartgpu::DevBuf<int64_t> d_dev_off;
     dartgpu::DevBuf<int32_t> d_rlen;
@@ -102,7 +104,6 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
 // NW jobs (op_off / flag_off are filled here). Results: c->o_op_off / c->o_ops (compacted, left-to-right columns).
 void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs);
 // the whole per-read path over the uploaded batch
-void run_pipeline(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out);   // host orchestration (A/B only)
 void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out);                              // device orchestration
 void free_device_pipe(void *p);
 

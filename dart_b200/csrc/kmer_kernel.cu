@@ -6,23 +6,25 @@
 // (PosDiff, rPos) and walks the equal-PosDiff runs with a counter `s` that is only reset when a run is
 // accepted (KmerAnalysis.cpp:147-163).  Only three numbers of each run are used: its size, its first rPos
 // and its last rPos.  So instead of materialising and sorting the pairs (up to ~500 k window positions):
-//   * the read gap's 8-mers (<= ~250) are sorted once in shared memory (warp bitonic sort);
-//   * the warp streams the genome window 32 positions at a time straight from the HBM-resident 2-bit
-//     reference, each lane forming its 8-mer with one funnel shift and looking it up by binary search;
-//   * matches update a shared-memory ring of per-diagonal {count, min rPos, max rPos}; a diagonal is final
-//     once the stream has passed it, so diagonals are retired in increasing PosDiff order — exactly the order
-//     of the reference's sorted walk — carrying `s` and `max_len` in registers.
+//   * the read gap's 8-mers (<= ~250) are sorted once in shared memory (block bitonic sort);
+//   * the block streams the genome window 256 positions at a time straight from the HBM-resident 2-bit
+//     reference, each thread forming its 8-mer with one funnel shift and looking it up by binary search;
+//   * matches update a shared-memory ring of per-diagonal {count, min rPos, max rPos} with shared-memory
+//     atomics; a diagonal is final once the stream has passed it, so warp 0 retires diagonals in increasing
+//     PosDiff order — exactly the order of the reference's sorted walk — carrying `s` and `max_len` in registers.
+// One block (8 warps) per job: windows reach 500 kb (MaxIntronSize) and a single warp streaming one is pure
+// latency (round-1 profile: 1.7 ms for one 115 kb window).
 // Algorithmic traffic: ceil(len2/4) bytes of reference + len1 bytes of read + 12 bytes of result per job.
 //
 // Quirks kept (only reachable with non-ACGT read symbols): only a literal 'N' breaks an 8-mer; other symbols
 // add 4 into the rolling id; the first id after a (re)start is unmasked; after an 'N' restart the rolling
-// window is one base late (KmerAnalysis.cpp:52, :60-75).  Those fragments take a sequential path on lane 0.
+// window is one base late (KmerAnalysis.cpp:52, :60-75).  Those fragments take a sequential path on thread 0.
 #include "dartgpu_internal.h"
 
 namespace dartgpu {
 
 constexpr unsigned FULLK = 0xffffffffu;
-constexpr int KMER_THREADS = 128;
+constexpr int KMER_THREADS = 256;
 
 // nst_nt4_table value of a device read code (0..3 ACGT, 8..11 acgt, 4 other, 5 'N')
 __device__ __forceinline__ uint32_t nt4(uint8_t c) { return (c & 4) ? 4u : (uint32_t)(c & 3); }
@@ -39,70 +41,69 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
        int tab_cap, int ring, dartgpu_kmer_hit *out)
 {
     extern __shared__ uint32_t smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int per_warp_words = tab_cap + (3 * ring) / 2;
-    uint32_t *tab = smem + (size_t)wib * per_warp_words;
-    uint16_t *cnt = reinterpret_cast<uint16_t *>(tab + tab_cap);
-    uint16_t *rmin = cnt + ring, *rmax = rmin + ring;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t *tab = smem;                       // tab_cap entries: id << 16 | read position
+    uint32_t *cnt = tab + tab_cap;              // ring of per-diagonal aggregates
+    uint32_t *rmin = cnt + ring, *rmax = rmin + ring;
+    __shared__ int s_nk, s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int job = warp; job < n_jobs; job += nwarps) {
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const KmerJobDev J = jobs[job];
         const int L1 = J.len1, L2 = J.len2;
         int best_r = 0, best_g = 0, best_len = 0;
-        __syncwarp();
+        __syncthreads();
         if (L1 >= 8 && L2 >= 8 && L1 <= tab_cap) {
             const uint8_t *s1 = codes + J.s1_off;
             // ---- 1. the read gap's 8-mer list ----
+            if (tid == 0) { s_bad = 0; s_nk = 0; }
+            __syncthreads();
             bool bad = false;
-            for (int p = lane; p < L1; p += 32) bad |= (s1[p] & 4) != 0;
-            bad = __any_sync(FULLK, bad);
-            int nk = 0;
-            if (!bad) {
-                nk = L1 - 7;
-                for (int p = lane; p < nk; p += 32) {
+            for (int p = tid; p < L1; p += KMER_THREADS) bad |= (s1[p] & 4) != 0;
+            if (bad) s_bad = 1;
+            __syncthreads();
+            if (!s_bad) {
+                for (int p = tid; p < L1 - 7; p += KMER_THREADS) {
                     uint32_t id = 0;
 #pragma unroll
                     for (int i = 0; i < 8; i++) id = (id << 2) | (s1[p + i] & 3u);
                     tab[p] = id << 16 | (uint32_t)p;
                 }
-            } else {
-                if (lane == 0) { // KmerAnalysis.cpp:34-80 step by step; ids above 16 bits can never match the genome
-                    int tail = 0, count = 0, head;
-                    while (count < 8 && tail < L1) { if (s1[tail++] != CODE_N) count++; else count = 0; }
-                    if (count == 8) {
-                        head = tail - 8;
-                        uint32_t wid = 0;
-                        for (int i = head; i < head + 8; i++) wid = (wid << 2) + nt4(s1[i]);
-                        if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
-                        for (head += 1; tail < L1; head++, tail++) {
-                            if (s1[tail] != CODE_N) {
-                                wid = ((wid & 0x3FFFu) << 2) + nt4(s1[tail]);
-                                if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
-                            } else {
-                                count = 0; tail++;
-                                while (count < 8 && tail < L1) { if (s1[tail++] != CODE_N) count++; else count = 0; }
-                                if (count != 8) break;
-                                head = tail - 8;
-                                wid = 0;
-                                for (int i = head; i < head + 8; i++) wid = (wid << 2) + nt4(s1[i]);
-                                if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
-                            }
+                if (tid == 0) s_nk = L1 - 7;
+            } else if (tid == 0) { // KmerAnalysis.cpp:34-80 step by step; ids above 16 bits can never match the genome
+                int nk = 0, tail = 0, count = 0, head;
+                while (count < 8 && tail < L1) { if (s1[tail++] != CODE_N) count++; else count = 0; }
+                if (count == 8) {
+                    head = tail - 8;
+                    uint32_t wid = 0;
+                    for (int i = head; i < head + 8; i++) wid = (wid << 2) + nt4(s1[i]);
+                    if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
+                    for (head += 1; tail < L1; head++, tail++) {
+                        if (s1[tail] != CODE_N) {
+                            wid = ((wid & 0x3FFFu) << 2) + nt4(s1[tail]);
+                            if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
+                        } else {
+                            count = 0; tail++;
+                            while (count < 8 && tail < L1) { if (s1[tail++] != CODE_N) count++; else count = 0; }
+                            if (count != 8) break;
+                            head = tail - 8;
+                            wid = 0;
+                            for (int i = head; i < head + 8; i++) wid = (wid << 2) + nt4(s1[i]);
+                            if (wid <= 0xFFFFu) tab[nk++] = wid << 16 | (uint32_t)head;
                         }
                     }
                 }
-                nk = __shfl_sync(FULLK, nk, 0);
+                s_nk = nk;
             }
-            __syncwarp();
+            __syncthreads();
+            const int nk = s_nk;
             if (nk > 0) {
                 int NP = 32;
                 while (NP < nk) NP <<= 1;
-                for (int i = nk + lane; i < NP; i += 32) tab[i] = 0xFFFFFFFFu;
-                __syncwarp();
+                for (int i = nk + tid; i < NP; i += KMER_THREADS) tab[i] = 0xFFFFFFFFu;
+                __syncthreads();
                 for (int k = 2; k <= NP; k <<= 1)
                     for (int j = k >> 1; j > 0; j >>= 1) {
-                        for (int i = lane; i < NP; i += 32) {
+                        for (int i = tid; i < NP; i += KMER_THREADS) {
                             int p = i ^ j;
                             if (p > i) {
                                 uint32_t x = tab[i], y = tab[p];
@@ -110,67 +111,60 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                                 if ((x > y) == up) { tab[i] = y; tab[p] = x; }
                             }
                         }
-                        __syncwarp();
+                        __syncthreads();
                     }
-                for (int s = lane; s < ring; s += 32) cnt[s] = 0;
-                __syncwarp();
+                for (int s = tid; s < ring; s += KMER_THREADS) { cnt[s] = 0; rmin[s] = 0xFFFFFFFFu; rmax[s] = 0; }
+                __syncthreads();
 
-                // ---- 2. stream the window; retire diagonals in increasing PosDiff order ----
+                // ---- 2. stream the window; warp 0 retires diagonals in increasing PosDiff order ----
                 const int ngk = L2 - 7;
                 const int dd_end = (ngk - 1) + L1 + 1; // one past the largest diagonal index (dd = gPos - rPos + L1)
-                int s_acc = 1, max_len = 0;
+                int s_acc = 1, max_len = 0;             // live in warp 0 only
                 int fin = 8;
-                for (int g0 = 0; g0 < ngk; g0 += 32) {
-                    const int g = g0 + lane;
-                    const bool has = g < ngk;
-                    uint32_t wid = has ? genome_kmer(ix, J.gpos + g) : 0u;
-                    int lo = 0, hi = nk;
-                    const uint32_t probe = wid << 16;
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (tab[mid] < probe) lo = mid + 1; else hi = mid; }
-                    bool hit = has && lo < nk && (tab[lo] >> 16) == wid;
-                    unsigned mm = __ballot_sync(FULLK, hit);
-                    while (mm) { // lanes with matches update the ring one after another (plain read-modify-write)
-                        int src = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        if (lane == src) {
-                            for (int e = lo; e < nk && (tab[e] >> 16) == wid; e++) {
-                                int r = (int)(tab[e] & 0xFFFFu);
-                                int slot = (g - r + L1) & (ring - 1);
-                                if (cnt[slot] == 0) { rmin[slot] = (uint16_t)r; rmax[slot] = (uint16_t)r; }
-                                else { if (r < rmin[slot]) rmin[slot] = (uint16_t)r; if (r > rmax[slot]) rmax[slot] = (uint16_t)r; }
-                                cnt[slot] = cnt[slot] + 1;
-                            }
+                for (int g0 = 0; g0 < ngk; g0 += KMER_THREADS) {
+                    const int g = g0 + tid;
+                    if (g < ngk) {
+                        const uint32_t wid = genome_kmer(ix, J.gpos + g);
+                        int lo = 0, hi = nk;
+                        const uint32_t probe = wid << 16;
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (tab[mid] < probe) lo = mid + 1; else hi = mid; }
+                        for (int e = lo; e < nk && (tab[e] >> 16) == wid; e++) {
+                            const uint32_t r = tab[e] & 0xFFFFu;
+                            const int slot = (g - (int)r + L1) & (ring - 1);
+                            atomicAdd(&cnt[slot], 1u); atomicMin(&rmin[slot], r); atomicMax(&rmax[slot], r);
                         }
-                        __syncwarp();
                     }
-                    const bool last_tile = g0 + 32 >= ngk;
-                    const int fin_end = last_tile ? dd_end : min(g0 + 40, dd_end);
-                    for (int base = fin; base < fin_end; base += 32) {
-                        int dd = base + lane;
-                        int slot = dd & (ring - 1);
-                        int c = dd < fin_end ? (int)cnt[slot] : 0;
-                        unsigned nz = __ballot_sync(FULLK, c > 0);
-                        while (nz) {
-                            int src = __ffs(nz) - 1;
-                            nz &= nz - 1;
-                            int sl = (base + src) & (ring - 1);
-                            int cc = cnt[sl], mn = rmin[sl], mx = rmax[sl];
-                            s_acc += cc - 1;
-                            int l = 8 + (mx - mn);
-                            if (l > max_len && s_acc > (l - 8) / 2) {
-                                best_r = mn; best_g = mn + (base + src - L1); best_len = l;
-                                max_len = l; s_acc = 1;
+                    __syncthreads();
+                    const bool last_tile = g0 + KMER_THREADS >= ngk;
+                    const int fin_end = last_tile ? dd_end : min(g0 + KMER_THREADS + 8, dd_end);
+                    if (warp == 0) {
+                        for (int base = fin; base < fin_end; base += 32) {
+                            const int dd = base + lane;
+                            const int slot = dd & (ring - 1);
+                            const uint32_t c = dd < fin_end ? cnt[slot] : 0u;
+                            unsigned nz = __ballot_sync(FULLK, c > 0);
+                            while (nz) {
+                                const int src = __ffs(nz) - 1;
+                                nz &= nz - 1;
+                                const int sl = (base + src) & (ring - 1);
+                                const int cc = (int)cnt[sl], mn = (int)rmin[sl], mx = (int)rmax[sl];
+                                s_acc += cc - 1;
+                                const int l = 8 + (mx - mn);
+                                if (l > max_len && s_acc > (l - 8) / 2) {
+                                    best_r = mn; best_g = mn + (base + src - L1); best_len = l;
+                                    max_len = l; s_acc = 1;
+                                }
                             }
+                            __syncwarp();
+                            if (c > 0) { cnt[slot] = 0; rmin[slot] = 0xFFFFFFFFu; rmax[slot] = 0; }
                         }
-                        __syncwarp();
-                        if (c > 0) cnt[slot] = 0;
-                        __syncwarp();
                     }
                     fin = fin_end;
+                    __syncthreads();
                 }
             }
         }
-        if (lane == 0) { out[job].rpos = best_r; out[job].gpos = best_g; out[job].len = best_len; }
+        if (tid == 0) { out[job].rpos = best_r; out[job].gpos = best_g; out[job].len = best_len; }
     }
 }
 
@@ -181,16 +175,14 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
 {
     if (n_jobs <= 0) return;
     int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
-    int ring = pow2_at_least(max_len1 + 32);
-    size_t per_warp = (size_t)(tab_cap + (3 * ring) / 2) * 4;
-    size_t smem = per_warp * (KMER_THREADS / 32);
+    int ring = pow2_at_least(max_len1 + KMER_THREADS + 32);
+    size_t smem = (size_t)(tab_cap + 3 * ring) * 4;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    int want = (n_jobs + (KMER_THREADS / 32) - 1) / (KMER_THREADS / 32);
-    int grid = want < 148 * 8 ? want : 148 * 8;
+    int grid = n_jobs < 148 * 8 ? n_jobs : 148 * 8;
     k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, n_jobs, tab_cap, ring, out);
 }
 

@@ -8,7 +8,7 @@
 // Execution model
 //   * a GROUP of 4 lanes owns one read at a time; 8 groups per warp run 8 independent FM chains.
 //     One rank query = one 128-bit load per lane = one 64-byte Occ block per group, each lane
-//     popcounting its own 32 symbols (3 POPC), combined with two xor-shuffles.
+//     popcounting its own 32 symbols (2 POPC: "equal to c" and "greater than c"), combined with xor-shuffles.
 //   * the nested loops of the reference (reads > search starts > extension steps) are flattened into a
 //     single loop whose every iteration performs exactly one rank step, so the 8 groups of a warp stay
 //     converged although their reads, search starts and match lengths differ.
@@ -20,6 +20,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include "dartgpu_internal.h"
+#include "rank.cuh"
 
 namespace dartgpu {
 
@@ -29,40 +30,15 @@ constexpr int RWORDS = DARTGPU_MAX_RLEN / 16;
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------------
-// rank primitives
+// rank primitives (rank.cuh holds the per-quarter arithmetic, unit-tested on the host)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fold_even(uint64_t x) { return (uint32_t)x | ((uint32_t)(x >> 32) << 1); }
-
-// A | C<<8 | G<<16 | T<<24 among the first n (0..32) symbols of a 32-symbol word (first symbol in the top bits)
-__device__ __forceinline__ uint32_t count_packed(uint64_t b, int n)
-{
-    const uint64_t M5 = 0x5555555555555555ull;
-    uint64_t keep = n > 0 ? (~0ull << (64 - 2 * n)) : 0ull;
-    uint64_t bk = b & keep;
-    uint64_t lo = bk & M5, hi = (bk >> 1) & M5;
-    int t = __popc(fold_even(hi & lo)), gt = __popc(fold_even(hi)), ct = __popc(fold_even(lo));
-    int g = gt - t, c = ct - t, a = n - gt - ct + t;
-    return (uint32_t)a | (uint32_t)c << 8 | (uint32_t)g << 16 | (uint32_t)t << 24;
-}
-
 __device__ __forceinline__ ulonglong2 load_quarter(const DevIndex &ix, uint64_t kk, int q)
 {
     return __ldg(ix.occ + ((kk >> 7) << 2) + q);
 }
 
-// lane q of the group returns Occ(symbol q, kk) — number of q in BWT[0..kk], kk already sentinel-adjusted
-__device__ __forceinline__ uint64_t finish_rank(ulonglong2 v, uint64_t kk, int q, unsigned gmask)
-{
-    int n = (int)(kk & 127) + 1 - 32 * q;
-    n = max(0, min(32, n));
-    uint32_t pc = count_packed(v.y, n);
-    pc += __shfl_xor_sync(gmask, pc, 1);
-    pc += __shfl_xor_sync(gmask, pc, 2);
-    return v.x + ((pc >> (8 * q)) & 0xffu);
-}
-
-__device__ __forceinline__ int rd_code(const uint32_t *pk, int p) { return (pk[p >> 4] >> ((p & 15) * 2)) & 3; }
-__device__ __forceinline__ int rd_amb(const uint16_t *am, int p) { return (am[p >> 4] >> (p & 15)) & 1; }
+// symbols of this lane's quarter that lie at or before block offset o (0..127)
+__device__ __forceinline__ int quarter_prefix(int o, int q) { return max(0, min(32, o + 1 - 32 * q)); }
 
 // stage one read in the group's shared-memory slot: 2 bits per base + 1 ambiguity bit per base
 __device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, int rl, uint32_t *pk, uint16_t *am,
@@ -90,26 +66,39 @@ __device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, in
 
 // ---------------------------------------------------------------------------------------------------
 // kernel 1: maximal exact-match segment search (IdentifySeedPairs' loop around BWT_Search, without locate)
+//
+// One forward-extension step per loop iteration (bwt_2occ4 + interval update, bwt_search.cpp:152-170), restated so
+// that a lane never needs more than two popcounts per block:
+//     n2   = Occ(c,l) - Occ(c,k)                       size of the new interval
+//     x1'  = L2[c] + 1 + Occ(c,k)                      its start on the reverse-complement strand
+//     x0'  = x0 + [sentinel in range] + sum_{j>c} (Occ(j,l) - Occ(j,k))      its start on the forward strand
+// Occ(j,.) = block header count (lane j holds it) + in-block count; the in-block parts of the 4 lanes are summed as
+// four 8-bit fields of one word (two xor-shuffles), the header differences travel as 32-bit values (interval widths
+// are < 2^32, checked at index load), only Occ(c,k)'s header needs a 64-bit shuffle.  7 SHFL + 4 POPC per step.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_search(DevIndex ix, SeedLaunch a)
 {
     __shared__ uint32_t s_pk[GROUPS_PER_CTA][RWORDS];
     __shared__ uint16_t s_am[GROUPS_PER_CTA][RWORDS];
+    __shared__ uint64_t s_L2[5];
 
     const int lane = threadIdx.x & 31, q = lane & 3;
     const unsigned gmask = 0xFu << (lane & ~3);
     const int grp = threadIdx.x >> 2;
+    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
+    __syncthreads();
     uint32_t *pk = s_pk[grp];
     uint16_t *am = s_am[grp];
     const int stride = gridDim.x * GROUPS_PER_CTA;
+    const uint64_t primary = ix.primary;
     int r = blockIdx.x * GROUPS_PER_CTA + grp;
 
     bool have_read = false, searching = false;
-    int rl = 0, start = 0, p = 0;
-    uint32_t nr = 0, nh = 0;
-    uint64_t x0 = 0, x1 = 0, x2 = 0;
-    unsigned long long st_steps = 0, st_blocks = 0;
+    int rl = 0, start = 0, p = 0, cw = -1;
+    uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0;
+    uint64_t x0 = 0, x1 = 0;
+    uint32_t st_steps = 0, st_splits = 0;
 
     for (;;) {
         if (!searching) {
@@ -119,59 +108,69 @@ k_search(DevIndex ix, SeedLaunch a)
                     if (r >= a.n_reads) { done = true; break; }
                     rl = a.rlen[r];
                     stage_read(a.codes, a.dev_off[r], rl, pk, am, q, gmask);
-                    start = 0; nr = 0; nh = 0; have_read = true;
+                    start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
                 }
-                while (start < rl - 13 && rd_amb(am, start)) start++;
+                while (start < rl - 13 && ((am[start >> 4] >> (start & 15)) & 1)) start++;
                 if (start < rl - 13) break;
                 if (q == 0) { a.nrec[r] = nr; a.nhits[r] = nh; }
                 have_read = false;
                 r += stride;
             }
             if (done) break;
-            int c0 = rd_code(pk, start);
-            x0 = ix.L2[c0] + 1; x1 = ix.L2[3 - c0] + 1; x2 = ix.L2[c0 + 1] - ix.L2[c0];
+            int c0 = (pk[start >> 4] >> ((start & 15) * 2)) & 3;
+            x0 = s_L2[c0] + 1; x1 = s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
             p = start + 1;
             searching = true;
         }
-        // ---- one forward-extension step (bwt_2occ4 + interval update, bwt_search.cpp:152-170) ----
-        bool end = false;
-        if (p >= rl || rd_amb(am, p)) end = true;
-        else {
-            uint64_t k = x1 - 1, l = x1 - 1 + x2;
-            uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-            ulonglong2 vk = load_quarter(ix, kk, q), vl = load_quarter(ix, ll, q);
-            st_steps++; st_blocks += ((kk >> 7) == (ll >> 7)) ? 1 : 2;
-            uint64_t tk = finish_rank(vk, kk, q, gmask), tl = finish_rank(vl, ll, q, gmask);
-            uint64_t n2 = tl - tk;
-            int c = 3 - rd_code(pk, p);
-            uint64_t n2c = __shfl_sync(gmask, n2, c, 4), tkc = __shfl_sync(gmask, tk, c, 4);
-            if (n2c == 0) end = true;
+        bool end = p >= rl;
+        if (!end) {
+            if ((p >> 4) != cw) { cw = p >> 4; wcode = pk[cw]; wamb = am[cw]; }
+            end = (wamb >> (p & 15)) & 1;
+        }
+        if (!end) {
+            const uint64_t k = x1 - 1, l = k + x2;
+            const uint64_t kk = k - (k >= primary), ll = l - (l >= primary);
+            const ulonglong2 vk = load_quarter(ix, kk, q), vl = load_quarter(ix, ll, q);
+            const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3);
+            st_steps++; st_splits += (kk >> 7) != (ll >> 7);
+            int eqk, gtk, eql, gtl;
+            count_eq_gt(vk.y, quarter_prefix((int)(kk & 127), q), c, eqk, gtk);
+            count_eq_gt(vl.y, quarter_prefix((int)(ll & 127), q), c, eql, gtl);
+            uint32_t pc = (uint32_t)eqk | (uint32_t)gtk << 8 | (uint32_t)eql << 16 | (uint32_t)gtl << 24;
+            pc += __shfl_xor_sync(gmask, pc, 1);
+            pc += __shfl_xor_sync(gmask, pc, 2);
+            const uint32_t D = (uint32_t)(vl.x - vk.x);
+            const uint32_t Dc = __shfl_sync(gmask, D, c, 4);
+            uint32_t Dab = q > c ? D : 0u;
+            Dab += __shfl_xor_sync(gmask, Dab, 1);
+            Dab += __shfl_xor_sync(gmask, Dab, 2);
+            const uint64_t cntk = __shfl_sync(gmask, vk.x, c, 4);
+            const uint32_t EK = pc & 0xffu, GK = (pc >> 8) & 0xffu, EL = (pc >> 16) & 0xffu, GL = pc >> 24;
+            const uint32_t n2 = Dc + EL - EK;
+            if (n2 == 0) end = true;
             else {
-                uint64_t above = q > c ? n2 : 0;
-                above += __shfl_xor_sync(gmask, above, 1);
-                above += __shfl_xor_sync(gmask, above, 2);
-                x0 = x0 + ((x1 <= ix.primary && x1 + x2 - 1 >= ix.primary) ? 1 : 0) + above;
-                x1 = ix.L2[c] + 1 + tkc;
-                x2 = n2c;
+                x0 += ((x1 <= primary && x1 + x2 - 1 >= primary) ? 1u : 0u) + (uint32_t)(Dab + GL - GK);
+                x1 = s_L2[c] + 1 + cntk + EK;
+                x2 = n2;
                 p++;
             }
         }
         if (end) {
             int len = p - start;
-            if (x2 <= (uint64_t)a.max_dup && len >= 16) { // bwt_search.cpp:173
+            if (x2 <= a.max_dup && len >= 16) { // bwt_search.cpp:173
                 if (q == 0 && (int)nr < a.cap_rec) {
-                    SearchRec rec; rec.x0 = x0; rec.freq = (uint32_t)x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
+                    SearchRec rec; rec.x0 = x0; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
                     a.recs[(int64_t)r * a.cap_rec + nr] = rec;
                 }
-                nr++; nh += (uint32_t)x2;
+                nr++; nh += x2;
                 start += len;
             } else start++;
             searching = false;
         }
     }
     if (q == 0 && st_steps) {
-        atomicAdd(&a.stats->ext_steps, st_steps);
-        atomicAdd(&a.stats->ext_blocks, st_blocks);
+        atomicAdd(&a.stats->ext_steps, (unsigned long long)st_steps);
+        atomicAdd(&a.stats->ext_blocks, (unsigned long long)st_steps + st_splits);
     }
 }
 
@@ -230,23 +229,30 @@ __global__ void k_expand(SeedLaunch a)
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_locate(DevIndex ix, SeedLaunch a, int64_t total)
 {
+    __shared__ uint64_t s_L2[5];
+    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
+    __syncthreads();
     const int lane = threadIdx.x & 31, q = lane & 3;
     const unsigned gmask = 0xFu << (lane & ~3);
     const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_CTA;
+    const uint64_t primary = ix.primary;
     unsigned long long st_lf = 0, st_hits = 0;
     for (int64_t s = (int64_t)blockIdx.x * GROUPS_PER_CTA + (threadIdx.x >> 2); s < total; s += ngroups) {
         uint64_t k = a.keys[s];
         uint32_t steps = 0;
-        while (k & ix.sa_mask) {
+        while (k & ix.sa_mask) {            // one LF step = one block: the symbol at k and its rank come from the same 64 bytes
             steps++;
-            if (k == ix.primary) { k = 0; continue; }
-            uint64_t kk = k - (k > ix.primary);
-            ulonglong2 v = load_quarter(ix, kk, q);
-            int o = (int)(kk & 127);
-            int c_here = (int)((v.y >> (62 - 2 * (o & 31))) & 3);
-            int c = __shfl_sync(gmask, c_here, o >> 5, 4);
-            uint64_t nxt = ix.L2[q] + finish_rank(v, kk, q, gmask);
-            k = __shfl_sync(gmask, nxt, c, 4);
+            if (k == primary) { k = 0; continue; }
+            const uint64_t kk = k - (k > primary);
+            const ulonglong2 v = load_quarter(ix, kk, q);
+            const int o = (int)(kk & 127);
+            const int c_here = (int)((v.y >> (62 - 2 * (o & 31))) & 3);
+            const int c = __shfl_sync(gmask, c_here, o >> 5, 4);
+            uint32_t eq = (uint32_t)count_eq(v.y, quarter_prefix(o, q), c);
+            eq += __shfl_xor_sync(gmask, eq, 1);
+            eq += __shfl_xor_sync(gmask, eq, 2);
+            const uint64_t cnt = __shfl_sync(gmask, v.x, c, 4);
+            k = s_L2[c] + cnt + eq;
         }
         uint64_t g = (uint64_t)steps + __ldg(ix.sa + (k >> ix.sa_shift));
         if (q == 0) {
