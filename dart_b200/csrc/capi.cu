@@ -391,6 +391,7 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
     ix.primary = v->primary; ix.seq_len = v->seq_len;
     for (int i = 0; i < 5; i++) ix.L2[i] = v->L2[i];
     ix.ref2 = c->d_ref2.p; ix.G = c->G; ix.chr_ends = c->d_ends.p; ix.n_ends = (int)c->ends.size();
+    ix.force64 = getenv("DARTGPU_FORCE_IDX64") != nullptr;
 }
 
 static bool slurp(const std::string &fn, std::vector<uint8_t> &buf)

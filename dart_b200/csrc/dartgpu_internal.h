@@ -31,6 +31,7 @@ struct DevIndex {
     int64_t G;
     const int64_t *chr_ends; // sorted last coordinates of every sequence on both strands (ChrLocMap keys)
     int n_ends;
+    int force64;             // tests only (DARTGPU_FORCE_IDX64=1): run the 64-bit interval kernels on a small index
 };
 
 struct SearchRec {           // one qualifying BWT_Search result: SA interval still to be located

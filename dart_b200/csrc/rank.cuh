@@ -3,7 +3,12 @@
 //
 // The forward-extension step of BWT_Search (/root/reference/src/bwt_search.cpp:152-170) needs, for the read's next base c,
 // only  Occ(c,·)  (new interval on the reverse strand) and  sum over symbols > c of Occ(·)  (shift of the forward-strand
-// interval), not the four counts bwt_occ4 produces: two indicator words, two POPCs per block.
+// interval), not the four counts bwt_occ4 produces.  Everything is done on 32-bit words (ncu, round 1: the first version
+// spent ~100 of its 305 warp-instructions per step emulating 64-bit shifts and logic):
+//   * the 2-bit symbols are split into two 32-bit bit-planes (low bits, high bits), both halves of the u64 folded into
+//     one word: symbol i < 16 sits at bit 31-2i, symbol 16+i at bit 30-2i;
+//   * "equal to c" and "greater than c" are 3-input boolean functions of the planes (LOP3);
+//   * "among the first n symbols" is an AND with a 33-entry mask table; 2 POPC per block.
 #pragma once
 #include <stdint.h>
 
@@ -24,29 +29,36 @@ RK_HD int popc32(uint32_t x)
 #endif
 }
 
-// indicators live on even bit positions only: fold the two halves of a u64 into one u32 -> a single POPC
-RK_HD uint32_t fold_even(uint64_t x) { return (uint32_t)x | ((uint32_t)(x >> 32) << 1); }
-
-// among the first n (0..32) symbols of b: eq = number equal to c, gt = number greater than c
-RK_HD void count_eq_gt(uint64_t b, int n, int c, int &eq, int &gt)
+// bit-planes of a 32-symbol word
+RK_HD void planes32(uint64_t b, uint32_t &lo, uint32_t &hi)
 {
-    const uint64_t M5 = 0x5555555555555555ull;
-    uint64_t v = n > 0 ? b >> (64 - 2 * n) : 0ull;   // the n symbols right-aligned; everything above reads as 0 = 'A'
-    uint64_t lo = v & M5, hi = (v >> 1) & M5;
-    uint64_t CH = (c & 2) ? M5 : 0ull, CL = (c & 1) ? M5 : 0ull;
-    uint64_t eqm = ~(hi ^ CH) & ~(lo ^ CL) & M5;
-    uint64_t gtm = (hi & ~CH) | (~(hi ^ CH) & lo & ~CL);
-    eq = popc32(fold_even(eqm)) - (c == 0 ? 32 - n : 0);
-    gt = popc32(fold_even(gtm));
+    const uint32_t bl = (uint32_t)b, bh = (uint32_t)(b >> 32);
+    lo = (bl & 0x55555555u) | ((bh << 1) & 0xAAAAAAAAu);
+    hi = ((bl >> 1) & 0x55555555u) | (bh & 0xAAAAAAAAu);
 }
 
-RK_HD int count_eq(uint64_t b, int n, int c)
+// plane bits of the first n (0..32) symbols
+RK_HD uint32_t prefix_mask32(int n)
 {
-    const uint64_t M5 = 0x5555555555555555ull;
-    uint64_t v = n > 0 ? b >> (64 - 2 * n) : 0ull;
-    uint64_t lo = v & M5, hi = (v >> 1) & M5;
-    uint64_t CH = (c & 2) ? M5 : 0ull, CL = (c & 1) ? M5 : 0ull;
-    return popc32(fold_even(~(hi ^ CH) & ~(lo ^ CL) & M5)) - (c == 0 ? 32 - n : 0);
+    uint32_t m = 0;
+    for (int j = 0; j < n; j++) m |= j < 16 ? 1u << (31 - 2 * j) : 1u << (30 - 2 * (j - 16));
+    return m;
 }
+
+// CH / CL: all-ones when bit 1 / bit 0 of c is set.  eq = #symbols == c, gt = #symbols > c under mask m.
+RK_HD void count_eq_gt32(uint32_t lo, uint32_t hi, uint32_t m, uint32_t CH, uint32_t CL, int &eq, int &gt)
+{
+    const uint32_t t1 = hi ^ CH, t2 = lo ^ CL;
+    eq = popc32(~t1 & ~t2 & m);
+    gt = popc32(((hi & ~CH) | (~t1 & lo & ~CL)) & m);
+}
+
+RK_HD int count_eq32(uint32_t lo, uint32_t hi, uint32_t m, uint32_t CH, uint32_t CL)
+{
+    return popc32(~(hi ^ CH) & ~(lo ^ CL) & m);
+}
+
+// the symbol at index j (0..31) of a quarter word
+RK_HD int symbol_at(uint64_t b, int j) { return (int)((b >> (62 - 2 * j)) & 3); }
 
 } // namespace dartgpu

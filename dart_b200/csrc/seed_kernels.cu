@@ -32,14 +32,6 @@ constexpr unsigned FULL = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------------
 // rank primitives (rank.cuh holds the per-quarter arithmetic, unit-tested on the host)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ ulonglong2 load_quarter(const DevIndex &ix, uint64_t kk, int q)
-{
-    return __ldg(ix.occ + ((kk >> 7) << 2) + q);
-}
-
-// symbols of this lane's quarter that lie at or before block offset o (0..127)
-__device__ __forceinline__ int quarter_prefix(int o, int q) { return max(0, min(32, o + 1 - 32 * q)); }
-
 // stage one read in the group's shared-memory slot: 2 bits per base + 1 ambiguity bit per base
 __device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, int rl, uint32_t *pk, uint16_t *am,
                                            int q, unsigned gmask)
@@ -74,30 +66,41 @@ __device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, in
 //     x0'  = x0 + [sentinel in range] + sum_{j>c} (Occ(j,l) - Occ(j,k))      its start on the forward strand
 // Occ(j,.) = block header count (lane j holds it) + in-block count; the in-block parts of the 4 lanes are summed as
 // four 8-bit fields of one word (two xor-shuffles), the header differences travel as 32-bit values (interval widths
-// are < 2^32, checked at index load), only Occ(c,k)'s header needs a 64-bit shuffle.  7 SHFL + 4 POPC per step.
+// are < 2^32, checked at index load).  IdxT = uint32_t when the whole text fits 32 bits (every tested genome and
+// BASELINE configs 1, 2, 5), uint64_t otherwise (3.1 Gbp: 2G = 6.2e9) — same code, narrower interval arithmetic.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tables(const DevIndex &ix, uint64_t *s_L2, uint32_t *s_mask)
+{
+    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
+    if (threadIdx.x < 33) s_mask[threadIdx.x] = prefix_mask32((int)threadIdx.x);
+    __syncthreads();
+}
+
+template <typename IdxT>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_search(DevIndex ix, SeedLaunch a)
 {
     __shared__ uint32_t s_pk[GROUPS_PER_CTA][RWORDS];
     __shared__ uint16_t s_am[GROUPS_PER_CTA][RWORDS];
     __shared__ uint64_t s_L2[5];
+    __shared__ uint32_t s_mask[33];
 
     const int lane = threadIdx.x & 31, q = lane & 3;
     const unsigned gmask = 0xFu << (lane & ~3);
     const int grp = threadIdx.x >> 2;
-    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
-    __syncthreads();
+    stage_tables(ix, s_L2, s_mask);
     uint32_t *pk = s_pk[grp];
     uint16_t *am = s_am[grp];
     const int stride = gridDim.x * GROUPS_PER_CTA;
-    const uint64_t primary = ix.primary;
+    const IdxT primary = (IdxT)ix.primary;
+    const char *occq = reinterpret_cast<const char *>(ix.occ + q);   // this lane's quarter of block 0
+    const int q32 = 32 * q - 1;
     int r = blockIdx.x * GROUPS_PER_CTA + grp;
 
     bool have_read = false, searching = false;
     int rl = 0, start = 0, p = 0, cw = -1;
     uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0;
-    uint64_t x0 = 0, x1 = 0;
+    IdxT x0 = 0, x1 = 0;
     uint32_t st_steps = 0, st_splits = 0;
 
     for (;;) {
@@ -118,7 +121,7 @@ k_search(DevIndex ix, SeedLaunch a)
             }
             if (done) break;
             int c0 = (pk[start >> 4] >> ((start & 15) * 2)) & 3;
-            x0 = s_L2[c0] + 1; x1 = s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
+            x0 = (IdxT)s_L2[c0] + 1; x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
             p = start + 1;
             searching = true;
         }
@@ -128,29 +131,36 @@ k_search(DevIndex ix, SeedLaunch a)
             end = (wamb >> (p & 15)) & 1;
         }
         if (!end) {
-            const uint64_t k = x1 - 1, l = k + x2;
-            const uint64_t kk = k - (k >= primary), ll = l - (l >= primary);
-            const ulonglong2 vk = load_quarter(ix, kk, q), vl = load_quarter(ix, ll, q);
-            const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3);
-            st_steps++; st_splits += (kk >> 7) != (ll >> 7);
+            const IdxT k = x1 - 1, l = k + x2;
+            const IdxT kk = k - (k >= primary), ll = l - (l >= primary);
+            // quarter q of block (kk >> 7): byte offset (kk >> 7) * 64 = (kk & ~127) >> 1
+            const ulonglong2 vk = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(kk & ~(IdxT)127) >> 1)));
+            const ulonglong2 vl = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(ll & ~(IdxT)127) >> 1)));
+            const uint32_t code = (wcode >> ((p & 15) * 2)) & 3u;      // c = 3 - code: complement
+            const int c = 3 - (int)code;
+            const uint32_t CH = (code & 2u) ? 0u : ~0u, CL = (code & 1u) ? 0u : ~0u;
+            st_steps++; st_splits += (uint32_t)((kk ^ ll) >> 7 != 0);
+            uint32_t lo, hi;
             int eqk, gtk, eql, gtl;
-            count_eq_gt(vk.y, quarter_prefix((int)(kk & 127), q), c, eqk, gtk);
-            count_eq_gt(vl.y, quarter_prefix((int)(ll & 127), q), c, eql, gtl);
+            planes32(vk.y, lo, hi);
+            count_eq_gt32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)kk & 127u) - q32))], CH, CL, eqk, gtk);
+            planes32(vl.y, lo, hi);
+            count_eq_gt32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)ll & 127u) - q32))], CH, CL, eql, gtl);
             uint32_t pc = (uint32_t)eqk | (uint32_t)gtk << 8 | (uint32_t)eql << 16 | (uint32_t)gtl << 24;
             pc += __shfl_xor_sync(gmask, pc, 1);
             pc += __shfl_xor_sync(gmask, pc, 2);
-            const uint32_t D = (uint32_t)(vl.x - vk.x);
+            const uint32_t D = (uint32_t)vl.x - (uint32_t)vk.x;
             const uint32_t Dc = __shfl_sync(gmask, D, c, 4);
             uint32_t Dab = q > c ? D : 0u;
             Dab += __shfl_xor_sync(gmask, Dab, 1);
             Dab += __shfl_xor_sync(gmask, Dab, 2);
-            const uint64_t cntk = __shfl_sync(gmask, vk.x, c, 4);
+            const IdxT cntk = __shfl_sync(gmask, (IdxT)vk.x, c, 4);
             const uint32_t EK = pc & 0xffu, GK = (pc >> 8) & 0xffu, EL = (pc >> 16) & 0xffu, GL = pc >> 24;
             const uint32_t n2 = Dc + EL - EK;
             if (n2 == 0) end = true;
             else {
-                x0 += ((x1 <= primary && x1 + x2 - 1 >= primary) ? 1u : 0u) + (uint32_t)(Dab + GL - GK);
-                x1 = s_L2[c] + 1 + cntk + EK;
+                x0 += (IdxT)(((x1 <= primary && (IdxT)(x1 + x2 - 1) >= primary) ? 1u : 0u) + (uint32_t)(Dab + GL - GK));
+                x1 = (IdxT)s_L2[c] + 1 + cntk + EK;
                 x2 = n2;
                 p++;
             }
@@ -174,12 +184,15 @@ k_search(DevIndex ix, SeedLaunch a)
     }
 }
 
+static bool fits32(const DevIndex &ix) { return !ix.force64 && ix.seq_len + 2 < (1ull << 32); }
+
 void launch_search(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
 {
     if (a.n_reads <= 0) return;
     int want = (a.n_reads + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
     int grid = want < 148 * 16 ? want : 148 * 16; // 16 CTAs of 128 threads fill an SM's 2048 thread slots
-    k_search<<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
+    if (fits32(ix)) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
+    else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -226,35 +239,40 @@ __global__ void k_expand(SeedLaunch a)
 // ---------------------------------------------------------------------------------------------------
 // kernel 2b: SA locate — bwt_sa / bwt_invPsi (bwt_search.cpp:119-137), one group per hit
 // ---------------------------------------------------------------------------------------------------
+template <typename IdxT>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_locate(DevIndex ix, SeedLaunch a, int64_t total)
 {
     __shared__ uint64_t s_L2[5];
-    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
-    __syncthreads();
+    __shared__ uint32_t s_mask[33];
+    stage_tables(ix, s_L2, s_mask);
     const int lane = threadIdx.x & 31, q = lane & 3;
     const unsigned gmask = 0xFu << (lane & ~3);
     const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_CTA;
-    const uint64_t primary = ix.primary;
+    const IdxT primary = (IdxT)ix.primary, sa_mask = (IdxT)ix.sa_mask;
+    const char *occq = reinterpret_cast<const char *>(ix.occ + q);
+    const int q32 = 32 * q - 1;
     unsigned long long st_lf = 0, st_hits = 0;
     for (int64_t s = (int64_t)blockIdx.x * GROUPS_PER_CTA + (threadIdx.x >> 2); s < total; s += ngroups) {
-        uint64_t k = a.keys[s];
+        IdxT k = (IdxT)a.keys[s];
         uint32_t steps = 0;
-        while (k & ix.sa_mask) {            // one LF step = one block: the symbol at k and its rank come from the same 64 bytes
+        while (k & sa_mask) {               // one LF step = one block: the symbol at k and its rank come from the same 64 bytes
             steps++;
             if (k == primary) { k = 0; continue; }
-            const uint64_t kk = k - (k > primary);
-            const ulonglong2 v = load_quarter(ix, kk, q);
-            const int o = (int)(kk & 127);
-            const int c_here = (int)((v.y >> (62 - 2 * (o & 31))) & 3);
-            const int c = __shfl_sync(gmask, c_here, o >> 5, 4);
-            uint32_t eq = (uint32_t)count_eq(v.y, quarter_prefix(o, q), c);
+            const IdxT kk = k - (k > primary);
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(kk & ~(IdxT)127) >> 1)));
+            const int o = (int)((uint32_t)kk & 127u);
+            const int c = __shfl_sync(gmask, symbol_at(v.y, o & 31), o >> 5, 4);
+            const uint32_t CH = (c & 2) ? ~0u : 0u, CL = (c & 1) ? ~0u : 0u;
+            uint32_t lo, hi;
+            planes32(v.y, lo, hi);
+            uint32_t eq = (uint32_t)count_eq32(lo, hi, s_mask[max(0, min(32, o - q32))], CH, CL);
             eq += __shfl_xor_sync(gmask, eq, 1);
             eq += __shfl_xor_sync(gmask, eq, 2);
-            const uint64_t cnt = __shfl_sync(gmask, v.x, c, 4);
-            k = s_L2[c] + cnt + eq;
+            const IdxT cnt = __shfl_sync(gmask, (IdxT)v.x, c, 4);
+            k = (IdxT)s_L2[c] + cnt + eq;
         }
-        uint64_t g = (uint64_t)steps + __ldg(ix.sa + (k >> ix.sa_shift));
+        uint64_t g = (uint64_t)steps + __ldg(ix.sa + ((uint64_t)k >> ix.sa_shift));
         if (q == 0) {
             uint32_t m = a.meta[s];
             a.keys[s] = seed_key(g, m >> 16, m & 0xFFFF);
@@ -276,7 +294,8 @@ void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, int64_t total
     k_expand<<<grid, 256, 0, st>>>(a);
     int64_t want = (total + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
     int g2 = (int)(want < 148 * 16 ? want : 148 * 16);
-    k_locate<<<g2, SEARCH_THREADS, 0, st>>>(ix, a, total);
+    if (fits32(ix)) k_locate<uint32_t><<<g2, SEARCH_THREADS, 0, st>>>(ix, a, total);
+    else k_locate<uint64_t><<<g2, SEARCH_THREADS, 0, st>>>(ix, a, total);
 }
 
 // ---------------------------------------------------------------------------------------------------

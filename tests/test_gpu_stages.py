@@ -52,6 +52,21 @@ def test_seeds_and_candidates_match_oracle(name, limit):
     M.close(); O.close()
 
 
+def test_64bit_interval_kernels(monkeypatch):
+    """Human-sized texts (2G = 6.2e9) need 64-bit SA intervals; the same kernels are instantiated for both widths.
+    Force the wide instantiation on a small index and require identical results."""
+    monkeypatch.setenv("DARTGPU_FORCE_IDX64", "1")
+    w = workload("c3")
+    O = po.Oracle(w["idx"])
+    M = capi.Mapper(w["idx"])
+    reads = read_fastq_seqs(w["r1"], 1500)
+    O.reset_counters()
+    _check_seeds(M, O, reads)
+    st, oc = M.stats(), O.counters()
+    assert (st["ext_steps"], st["ext_blocks"], st["lf_steps"], st["hits"]) == (oc["ext_steps"], oc["ext_blocks"], oc["lf_steps"], oc["hits"])
+    M.close(); O.close()
+
+
 def test_repeat_rich_genome_with_max_dup_10000():
     w = workload("c5")
     O = po.Oracle(w["idx"])
