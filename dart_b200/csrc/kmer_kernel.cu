@@ -7,11 +7,13 @@
 // accepted (KmerAnalysis.cpp:147-163).  Only three numbers of each run are used: its size, its first rPos
 // and its last rPos.  So instead of materialising and sorting the pairs (up to ~500 k window positions):
 //   * the read gap's 8-mers (<= ~250) are sorted once in shared memory (block bitonic sort);
-//   * the block streams the genome window 256 positions at a time straight from the HBM-resident 2-bit
-//     reference, each thread forming its 8-mer with one funnel shift and looking it up by binary search;
+//   * the block streams the genome window 1024 positions at a time straight from the HBM-resident 2-bit
+//     reference, each thread forming four 8-mers (one funnel shift each, all loads in flight first) and looking
+//     them up by four interleaved binary searches;
 //   * matches update a shared-memory ring of per-diagonal {count, min rPos, max rPos} with shared-memory
-//     atomics; a diagonal is final once the stream has passed it, so warp 0 retires diagonals in increasing
-//     PosDiff order — exactly the order of the reference's sorted walk — carrying `s` and `max_len` in registers.
+//     atomics; a diagonal is final once the stream has passed it: all warps ballot which diagonals are occupied
+//     (almost none are), warp 0 retires the occupied ones in increasing PosDiff order — exactly the order of the
+//     reference's sorted walk — carrying `s` and `max_len` in registers.
 // One block (8 warps) per job: windows reach 500 kb (MaxIntronSize) and a single warp streaming one is pure
 // latency (round-1 profile: 1.7 ms for one 115 kb window).
 // Algorithmic traffic: ceil(len2/4) bytes of reference + len1 bytes of read + 12 bytes of result per job.
@@ -25,6 +27,8 @@ namespace dartgpu {
 
 constexpr unsigned FULLK = 0xffffffffu;
 constexpr int KMER_THREADS = 256;
+constexpr int KMER_PPT = 4;                       // window positions per thread and tile
+constexpr int KMER_TILE = KMER_THREADS * KMER_PPT;
 
 // nst_nt4_table value of a device read code (0..3 ACGT, 8..11 acgt, 4 other, 5 'N')
 __device__ __forceinline__ uint32_t nt4(uint8_t c) { return (c & 4) ? 4u : (uint32_t)(c & 3); }
@@ -44,6 +48,7 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
     uint32_t *tab = smem;                       // tab_cap entries: id << 16 | read position
     uint32_t *cnt = tab + tab_cap;              // ring of per-diagonal aggregates
     uint32_t *rmin = cnt + ring, *rmax = rmin + ring;
+    uint32_t *bal = rmax + ring;                // occupancy bitmaps of the diagonals being retired
     __shared__ int s_nk, s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -116,47 +121,73 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                 for (int s = tid; s < ring; s += KMER_THREADS) { cnt[s] = 0; rmin[s] = 0xFFFFFFFFu; rmax[s] = 0; }
                 __syncthreads();
 
-                // ---- 2. stream the window; warp 0 retires diagonals in increasing PosDiff order ----
+                // ---- 2. stream the window KMER_TILE positions at a time; retire diagonals in increasing PosDiff order ----
                 const int ngk = L2 - 7;
                 const int dd_end = (ngk - 1) + L1 + 1; // one past the largest diagonal index (dd = gPos - rPos + L1)
                 int s_acc = 1, max_len = 0;             // live in warp 0 only
                 int fin = 8;
-                for (int g0 = 0; g0 < ngk; g0 += KMER_THREADS) {
-                    const int g = g0 + tid;
-                    if (g < ngk) {
-                        const uint32_t wid = genome_kmer(ix, J.gpos + g);
-                        int lo = 0, hi = nk;
-                        const uint32_t probe = wid << 16;
-                        while (lo < hi) { int mid = (lo + hi) >> 1; if (tab[mid] < probe) lo = mid + 1; else hi = mid; }
-                        for (int e = lo; e < nk && (tab[e] >> 16) == wid; e++) {
-                            const uint32_t r = tab[e] & 0xFFFFu;
-                            const int slot = (g - (int)r + L1) & (ring - 1);
-                            atomicAdd(&cnt[slot], 1u); atomicMin(&rmin[slot], r); atomicMax(&rmax[slot], r);
+                int steps = 0;
+                for (int t = nk; t > 0; t >>= 1) steps++;       // iterations of a lower_bound over nk entries
+                for (int g0 = 0; g0 < ngk; g0 += KMER_TILE) {
+                    // four positions per thread: all eight reference words are in flight before the first lookup
+                    uint32_t wid[KMER_PPT];
+                    int lo[KMER_PPT], hi[KMER_PPT];
+#pragma unroll
+                    for (int i = 0; i < KMER_PPT; i++) {
+                        const int g = g0 + tid + KMER_THREADS * i;
+                        wid[i] = g < ngk ? genome_kmer(ix, J.gpos + g) : 0u;
+                        lo[i] = 0; hi[i] = g < ngk ? nk : 0;
+                    }
+                    for (int it = 0; it < steps; it++) {
+#pragma unroll
+                        for (int i = 0; i < KMER_PPT; i++) {
+                            if (lo[i] < hi[i]) { int mid = (lo[i] + hi[i]) >> 1; if (tab[mid] < (wid[i] << 16)) lo[i] = mid + 1; else hi[i] = mid; }
                         }
                     }
+#pragma unroll
+                    for (int i = 0; i < KMER_PPT; i++) {
+                        const int g = g0 + tid + KMER_THREADS * i;
+                        if (g < ngk)
+                            for (int e = lo[i]; e < nk && (tab[e] >> 16) == wid[i]; e++) {
+                                const uint32_t r = tab[e] & 0xFFFFu;
+                                const int slot = (g - (int)r + L1) & (ring - 1);
+                                atomicAdd(&cnt[slot], 1u); atomicMin(&rmin[slot], r); atomicMax(&rmax[slot], r);
+                            }
+                    }
                     __syncthreads();
-                    const bool last_tile = g0 + KMER_THREADS >= ngk;
-                    const int fin_end = last_tile ? dd_end : min(g0 + KMER_THREADS + 8, dd_end);
-                    if (warp == 0) {
-                        for (int base = fin; base < fin_end; base += 32) {
-                            const int dd = base + lane;
-                            const int slot = dd & (ring - 1);
-                            const uint32_t c = dd < fin_end ? cnt[slot] : 0u;
-                            unsigned nz = __ballot_sync(FULLK, c > 0);
-                            while (nz) {
-                                const int src = __ffs(nz) - 1;
-                                nz &= nz - 1;
-                                const int sl = (base + src) & (ring - 1);
-                                const int cc = (int)cnt[sl], mn = (int)rmin[sl], mx = (int)rmax[sl];
-                                s_acc += cc - 1;
-                                const int l = 8 + (mx - mn);
-                                if (l > max_len && s_acc > (l - 8) / 2) {
-                                    best_r = mn; best_g = mn + (base + src - L1); best_len = l;
-                                    max_len = l; s_acc = 1;
+                    const bool last_tile = g0 + KMER_TILE >= ngk;
+                    const int fin_end = last_tile ? dd_end : min(g0 + KMER_TILE + 8, dd_end);
+                    const int nchunks = (fin_end - fin + 31) >> 5;
+                    for (int cb = warp; cb < nchunks; cb += KMER_THREADS / 32) {   // all warps: which 32-diagonal chunks are occupied
+                        const int dd = fin + cb * 32 + lane;
+                        const unsigned b = __ballot_sync(FULLK, dd < fin_end && cnt[dd & (ring - 1)] > 0);
+                        if (lane == 0) bal[cb] = b;
+                    }
+                    __syncthreads();
+                    if (warp == 0) {                                               // warp 0: the occupied ones, in order
+                        for (int cb = 0; cb < nchunks; cb += 32) {
+                            const unsigned mine = cb + lane < nchunks ? bal[cb + lane] : 0u;
+                            unsigned nzc = __ballot_sync(FULLK, mine != 0);
+                            while (nzc) {
+                                const int ci = __ffs(nzc) - 1;
+                                nzc &= nzc - 1;
+                                unsigned word = __shfl_sync(FULLK, mine, ci);
+                                const int base = fin + (cb + ci) * 32;
+                                while (word) {
+                                    const int src = __ffs(word) - 1;
+                                    word &= word - 1;
+                                    const int sl = (base + src) & (ring - 1);
+                                    const int cc = (int)cnt[sl], mn = (int)rmin[sl], mx = (int)rmax[sl];
+                                    s_acc += cc - 1;
+                                    const int l = 8 + (mx - mn);
+                                    if (l > max_len && s_acc > (l - 8) / 2) {
+                                        best_r = mn; best_g = mn + (base + src - L1); best_len = l;
+                                        max_len = l; s_acc = 1;
+                                    }
+                                    __syncwarp();
+                                    if (lane == 0) { cnt[sl] = 0; rmin[sl] = 0xFFFFFFFFu; rmax[sl] = 0; }
                                 }
                             }
-                            __syncwarp();
-                            if (c > 0) { cnt[slot] = 0; rmin[slot] = 0xFFFFFFFFu; rmax[slot] = 0; }
                         }
                     }
                     fin = fin_end;
@@ -175,8 +206,8 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
 {
     if (n_jobs <= 0) return;
     int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
-    int ring = pow2_at_least(max_len1 + KMER_THREADS + 32);
-    size_t smem = (size_t)(tab_cap + 3 * ring) * 4;
+    int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
+    size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8) * 4;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

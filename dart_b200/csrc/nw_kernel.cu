@@ -13,8 +13,8 @@
 // is swept in strips of 32 rows; inside a strip the warp advances along anti-diagonals: lane l owns row l of
 // the strip and at step t computes column t-l.  Left neighbours stay in registers, upper neighbours arrive
 // by shuffle from lane l-1, the genome base is handed down the lanes systolically.  Integer pipes only:
-// ~20 integer ops + 4 shuffles per cell-step.  Two traceback bits per cell go to global scratch; lane 0
-// walks them back.
+// ~20 integer ops + 4 shuffles per cell-step.  Two traceback bits per cell: in registers for single-strip jobs
+// (m <= 32, n <= 64 — walked back with shuffles), in global scratch for larger ones (lane 0 walks them back).
 #include "dartgpu_internal.h"
 
 namespace dartgpu {
@@ -41,6 +41,57 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
     for (int job = warp; job < n_jobs; job += nwarps) {
         const NwJobDev J = jobs[job];
         const int m = J.m, n = J.n;
+        if (m <= 32 && n <= 64) {
+            // ---- small job (the overwhelming majority: a mismatch or a short indel between two seeds): one strip, the
+            // traceback bits stay in registers (2 x 64 bits per row) and are walked back with shuffles — no global
+            // round trips between the sweep and the traceback.
+            const int i = lane + 1;
+            const bool rowok = i <= m;
+            int a = rowok ? (int)codes[J.s1_off + lane] : 7;
+            a = (a & 4) ? 7 : (a & 3);
+            const int b0reg = lane < n ? ref_base(ix, J.gpos + lane) : 0;
+            const int b1reg = lane + 32 < n ? ref_base(ix, J.gpos + lane + 32) : 0;
+            int Sl = -2 - i, Rl = NW_NEG, Sd = (i == 1) ? 0 : -2 - (i - 1);
+            int So = 0, To = 0, bo = 0;
+            uint64_t flo = 0, fhi = 0;
+            const int steps = n + m - 1;
+            for (int t = 0; t < steps; t++) {
+                int Su = __shfl_up_sync(FULLM, So, 1);
+                int Tu = __shfl_up_sync(FULLM, To, 1);
+                int b = __shfl_up_sync(FULLM, bo, 1);
+                const int b0 = t < 32 ? __shfl_sync(FULLM, b0reg, t) : __shfl_sync(FULLM, b1reg, t - 32);
+                const int j = t - lane + 1;
+                if (lane == 0) { Su = -2 - j; Tu = NW_NEG; b = b0; }
+                if (rowok && j >= 1 && j <= n) {
+                    int R = max(Rl - 1, Sl - 3);
+                    int T = max(Tu - 1, Su - 3);
+                    int h = max(Sd + (a == b ? 3 : -3), max(R, T));
+                    int S = (h / 2) * 2;
+                    uint64_t f = (S == R ? 1ull : 0ull) | (S == T ? 2ull : 0ull);
+                    if (j <= 32) flo |= f << (2 * (j - 1)); else fhi |= f << (2 * (j - 33));
+                    Sd = Su; Sl = S; Rl = R;
+                    So = S; To = T; bo = b;
+                }
+            }
+            int ti = m, tj = n, k = 0;                       // identical in every lane: the walk is warp-uniform
+            int64_t pos = J.op_off + m + n;
+            while (ti > 0 || tj > 0) {
+                int op;
+                if (ti == 0) op = 1;
+                else if (tj == 0) op = 2;
+                else {
+                    uint64_t w = __shfl_sync(FULLM, tj <= 32 ? flo : fhi, ti - 1);
+                    uint32_t f = (uint32_t)(w >> (2 * ((tj - 1) & 31))) & 3u;
+                    op = (f & 1u) ? 1 : ((f & 2u) ? 2 : 0);
+                }
+                --pos;
+                if (lane == 0) ops[pos] = (uint8_t)op;
+                k++;
+                if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
+            }
+            if (lane == 0) nops[job] = k;
+            continue;
+        }
         const int wpr = (n + 15) >> 4;
         uint32_t *fl = flags + J.flag_off;
 

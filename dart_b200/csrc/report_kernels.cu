@@ -93,13 +93,22 @@ __global__ void k_nw_offsets(NwJobDev *jobs, int n, const int64_t *o_ops, const 
                              unsigned long long *cells)
 {
     unsigned long long mine = 0;
+    int mx = 0, multi = 0;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         jobs[j].op_off = o_ops[j]; jobs[j].flag_off = o_flags[j]; jobs[j].aux_off = o_aux[j];
-        atomicMax(max_n, jobs[j].n);
-        if (jobs[j].m > 32) atomicOr(any_multi, 1);
+        mx = max(mx, jobs[j].n);
+        multi |= jobs[j].m > 32 || jobs[j].n > 64;          // leaves the register-resident path of k_nw
         mine += (unsigned long long)jobs[j].m * jobs[j].n;
     }
-    if (mine) atomicAdd(cells, mine);
+    // one atomic per warp, not per job (round-1 launch list: 427 us of contention on two addresses)
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    multi = __any_sync(0xffffffffu, multi);
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0) {
+        if (mx > 0) atomicMax(max_n, mx);
+        if (multi) atomicOr(any_multi, 1);
+        if (mine) atomicAdd(cells, mine);
+    }
 }
 
 __global__ void k_kmer_work(const KmerJobDev *jobs, int n, unsigned long long *acc)
