@@ -32,7 +32,7 @@ __global__ void k_cand_init(int n_reads, const int64_t *seed_off, const int64_t 
             int64_t pd = key_gpos(key) - key_rpos(key);
             c.PosDiff = pd < 0 ? 0 : pd;
             c.pos = 0; c.sv_off = 0; c.cig_off = 0; c.text_off = 0; c.sv_n = 0; c.sv_cap = 0; c.cig_cap = 0; c.cig_n = 0; c.text_len = 0;
-            c.AlnScore = 0; c.mis = 0; c.chr = 0; c.live = 0; c.skip = 0; c.dir = 0; c.pad = 0;
+            c.AlnScore = 0; c.mis = 0; c.chr = 0; c.n_ext = 0; c.live = 0; c.skip = 0; c.dir = 0; c.pad = 0;
             cs[co + k] = c;
         }
     }
@@ -68,13 +68,28 @@ __global__ void k_set_sv_off(int64_t ncand, CandState *cs, const int64_t *off)
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += (int64_t)gridDim.x * blockDim.x) cs[c].sv_off = off[c];
 }
 
-__global__ void k_phase(Env E, int64_t ncand, int which)
+// One thread per candidate.  The candidate's record is worked on in registers and its seeds, when few (the normal
+// case: 1-4 seeds), in a shared-memory slot; larger candidates work in place on their HBM slice.
+constexpr int STAGE_SEEDS = 8;
+template <int WHICH>
+__global__ void __launch_bounds__(TPB) k_phase(Env E, int64_t ncand)
 {
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += (int64_t)gridDim.x * blockDim.x) {
-        if (which == 0) phase_a(E, (int)c);
-        else if (which == 1) phase_b(E, (int)c);
-        else if (which == 2) phase_c(E, (int)c);
-        else phase_d(E, (int)c);
+    __shared__ RSeed s_slot[TPB * STAGE_SEEDS];
+    for (int64_t cid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cid < ncand; cid += (int64_t)gridDim.x * blockDim.x) {
+        CandState c = E.cs[cid];
+        if (!c.live) { if (WHICH == 3) { E.cs[cid].AlnScore = 0; E.cs[cid].cig_n = 0; E.cs[cid].text_len = 0; } continue; }
+        RSeed *g = E.pool + c.sv_off, *sv = g;
+        const bool staged = phase_seed_bound(c, WHICH) <= STAGE_SEEDS;
+        if (staged) {
+            sv = s_slot + threadIdx.x * STAGE_SEEDS;
+            if (WHICH != 0) for (int i = 0; i < c.sv_n; i++) sv[i] = g[i];
+        }
+        if (WHICH == 0) phase_a(E, c, sv);
+        else if (WHICH == 1) phase_b(E, c, sv);
+        else if (WHICH == 2) phase_c(E, c, sv);
+        else phase_d(E, c, sv);
+        if (staged) for (int i = 0; i < c.sv_n; i++) g[i] = sv[i];
+        E.cs[cid] = c;
     }
 }
 
@@ -335,7 +350,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     E.kjobs = D->kjobs.p; E.kjob_count = D->counters.p + 0; E.khits = D->khits.p;
 
     // ---- phase A -> 8-mer re-seeding ----
-    k_phase<<<grid_for(ncand), TPB, 0, st>>>(E, ncand, 0);
+    k_phase<0><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
@@ -354,7 +369,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
 
     // ---- phase B -> NW of every gap against both flanks ----
     E.njobs = D->jobsB.p; E.njob_count = D->counters.p + 1;
-    k_phase<<<grid_for(ncand), TPB, 0, st>>>(E, ncand, 1);
+    k_phase<1><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
@@ -364,7 +379,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     // ---- phase C -> NW of every non-simple pair ----
     E.ops = D->opsB.p; E.nops = D->nopsB.p; E.done_jobs = D->jobsB.p; E.xscratch = D->aux.p;
     E.njobs = D->jobsC.p; E.njob_count = D->counters.p + 2;
-    k_phase<<<grid_for(ncand), TPB, 0, st>>>(E, ncand, 2);
+    k_phase<2><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
@@ -379,7 +394,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     k_set_cig_off<<<grid_for(ncand), TPB, 0, st>>>(ncand, D->cs.p, D->cig_off.p);
     D->cig.reserve(cig_total + 1);
     E.ops = D->opsC.p; E.nops = D->nopsC.p; E.done_jobs = D->jobsC.p; E.cig = D->cig.p;
-    k_phase<<<grid_for(ncand), TPB, 0, st>>>(E, ncand, 3);
+    k_phase<3><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
 
     // ---- per read / pair: best, mate rescue, flags, MAPQ; record layout ----

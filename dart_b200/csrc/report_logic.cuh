@@ -50,6 +50,7 @@ struct CandState {        // AlignmentCandidate_t + AlignmentReport_t of one can
     int32_t sv_n, sv_cap;
     int32_t cig_cap, cig_n, text_len;
     int32_t AlnScore, mis, chr;
+    int32_t n_ext;        // gaps sent to NW by phase B (bounds the seeds phase C can add)
     uint8_t live, skip, dir, pad;
 };
 
@@ -242,14 +243,23 @@ HDN void pair_and_prune(CandState *v1, int n1, CandState *v2, int n2, bool paire
 // seeds one live candidate can ever hold: n after the filters, + (n-1) re-seeds, + 2 per gap, + one pair per gap
 HD int seed_capacity(int count) { return count <= 1 ? 1 : 12 * count + 4; }   // a lone seed has no gaps to fill
 
+// Upper bound of the seeds (incl. scratch) a phase touches, from what is known when it starts: lets the kernels run the
+// phase on a small shared-memory copy of the candidate's seeds instead of its HBM slice (ncu, round 1: phase C spent
+// 95 % of its time on store-to-load round trips through L2).
+HD int phase_seed_bound(const CandState &c, int which)
+{
+    if (which == 0) return c.seed_count + (8 * c.seed_count + 39) / 40;      // + the rPos sort scratch behind the seeds
+    if (which == 1) return 2 * c.sv_n;                                       // one re-seed per gap
+    if (which == 2) return 2 * (c.sv_n + 2 * c.n_ext);                       // two seeds per aligned gap, one pair per gap
+    return c.sv_n;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // phase A: filters + windows for 8-mer re-seeding
 // ---------------------------------------------------------------------------------------------------
-HDN void phase_a(const Env &E, int cid)
+HDN void phase_a(const Env &E, CandState &c, RSeed *sv)
 {
-    CandState &c = E.cs[cid];
     if (!c.live) return;
-    RSeed *sv = E.pool + c.sv_off;
     int32_t n = c.seed_count;
     for (int s = 0; s < n; s++) {
         uint64_t key = E.keys[c.seed_begin + s];
@@ -279,11 +289,9 @@ HDN void phase_a(const Env &E, int cid)
 // ---------------------------------------------------------------------------------------------------
 // phase B: accept re-seeds; gaps to be aligned against both flanks
 // ---------------------------------------------------------------------------------------------------
-HDN void phase_b(const Env &E, int cid)
+HDN void phase_b(const Env &E, CandState &c, RSeed *sv)
 {
-    CandState &c = E.cs[cid];
     if (!c.live) return;
-    RSeed *sv = E.pool + c.sv_off;
     int32_t n = c.sv_n;
     const int64_t coff = E.code_off[c.read];
     const int num = n;
@@ -303,6 +311,7 @@ HDN void phase_b(const Env &E, int cid)
     }
     for (int i = 0; i < n; i++) sv[i].job = -1;
     if (added) sort_seeds(sv, n);
+    int n_ext = 0;
     for (int i = 1; i < n; i++) {
         if ((int)(sv[i].PosDiff - sv[i - 1].PosDiff) > E.P.min_intron && sv[i].rPos > (sv[i - 1].rPos + sv[i - 1].rLen)) {
             int rGaps = sv[i].rPos - (sv[i - 1].rPos + sv[i - 1].rLen);
@@ -312,9 +321,11 @@ HDN void phase_b(const Env &E, int cid)
             NwJobDev b = a; b.gpos = sv[i].gPos - rGaps;
             E.njobs[id] = a; E.njobs[id + 1] = b;
             sv[i].job = id;
+            n_ext++;
         }
     }
     c.sv_n = n;
+    c.n_ext = n_ext;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -538,11 +549,9 @@ HD bool simple_enough(const Env &E, const uint8_t *rc, const RSeed &sp, int *n_o
 // ---------------------------------------------------------------------------------------------------
 // phase C: gapped partitions -> seeds, splice-motif snapping, normal pairs, pair alignments to run
 // ---------------------------------------------------------------------------------------------------
-HDN void phase_c(const Env &E, int cid)
+HDN void phase_c(const Env &E, CandState &c, RSeed *sv)
 {
-    CandState &c = E.cs[cid];
     if (!c.live) return;
-    RSeed *sv = E.pool + c.sv_off;
     int32_t n = c.sv_n;
     const uint8_t *rc = E.codes + E.code_off[c.read];
     const int num = n;
@@ -635,12 +644,10 @@ HDN bool local_quality_ok(const Env &E, const uint8_t *s1, int64_t gpos, const A
 
 HD int digits10(int v) { int d = 1; while (v >= 10) { v /= 10; d++; } return d; }
 
-HDN void phase_d(const Env &E, int cid)
+HDN void phase_d(const Env &E, CandState &c, RSeed *sv)
 {
-    CandState &c = E.cs[cid];
     c.AlnScore = 0; c.cig_n = 0; c.text_len = 0;
     if (!c.live || c.skip) return;
-    RSeed *sv = E.pool + c.sv_off;
     const int n = c.sv_n;
     const uint8_t *rc = E.codes + E.code_off[c.read];
     CigW cv; cv.p = E.cig + c.cig_off; cv.n = 0; cv.cap = c.cig_cap;

@@ -141,7 +141,7 @@ int main(int argc, char **argv)
         }
     };
 
-    for (int c = 0; c < ncand; c++) phase_a(E, c);
+    for (int c = 0; c < ncand; c++) phase_a(E, cs[c], pool.data() + cs[c].sv_off);
     for (int j = 0; j < nk; j++) {
         std::string g = genome(kjobs[j].gpos, kjobs[j].len2);
         int64_t o3[3];
@@ -149,18 +149,18 @@ int main(int argc, char **argv)
         khits[j].rpos = (int32_t)o3[0]; khits[j].gpos = (int32_t)o3[1]; khits[j].len = (int32_t)o3[2];
     }
     E.njobs = jobsB.data(); E.njob_count = &nB;
-    for (int c = 0; c < ncand; c++) phase_b(E, c);
+    for (int c = 0; c < ncand; c++) phase_b(E, cs[c], pool.data() + cs[c].sv_off);
     std::vector<uint8_t> opsB, opsC; std::vector<int32_t> nopsB, nopsC, aux;
     run_nw(jobsB, nB, opsB, nopsB, &aux);
     E.ops = opsB.data(); E.nops = nopsB.data(); E.done_jobs = jobsB.data(); E.xscratch = aux.data();
     E.njobs = jobsC.data(); E.njob_count = &nC;
-    for (int c = 0; c < ncand; c++) phase_c(E, c);
+    for (int c = 0; c < ncand; c++) phase_c(E, cs[c], pool.data() + cs[c].sv_off);
     run_nw(jobsC, nC, opsC, nopsC, nullptr);
     int64_t cig_total = 0;
     for (auto &c : cs) { c.cig_off = cig_total; cig_total += c.live && !c.skip ? c.cig_cap : 0; }
     std::vector<int32_t> cig(cig_total + 1);
     E.ops = opsC.data(); E.nops = nopsC.data(); E.done_jobs = jobsC.data(); E.cig = cig.data();
-    for (int c = 0; c < ncand; c++) { phase_d(E, c); if (cs[c].cig_n < 0) { fprintf(stderr, "CIGAR capacity overflow\n"); return 1; } }
+    for (int c = 0; c < ncand; c++) { phase_d(E, cs[c], pool.data() + cs[c].sv_off); if (cs[c].cig_n < 0) { fprintf(stderr, "CIGAR capacity overflow\n"); return 1; } }
 
     // ---- final pass ----
     std::vector<dartgpu_read_result> rr(n); std::vector<ReadOut> ro(n);
