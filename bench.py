@@ -22,6 +22,8 @@ import sys
 import threading
 import time
 
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -34,6 +36,7 @@ MIS = os.environ.get("DART_BENCH_MIS")  # None = as BASELINE names the config (n
 # Default = BASELINE config[1] (what `metric` is quoted on at 1 GPU).  DART_BENCH_WORKLOAD=c3 switches to a scaled
 # config[2] (multi-contig genome with gene models, spliced pairs; DART_BENCH_SCALE x 3.1 Gbp) whose Occ table no longer
 # fits L2 — used for the HBM-bound roofline of k_search in profiles/, never for the headline line.
+CONTEXTS = int(os.environ.get("DART_BENCH_CONTEXTS", 4))
 WORKLOAD = os.environ.get("DART_BENCH_WORKLOAD", "c2")
 SCALE = float(os.environ.get("DART_BENCH_SCALE", "0.06"))
 
@@ -181,6 +184,7 @@ def main():
     import torch
     import torch.distributed as dist
     from dart_b200 import capi
+    from dart_b200.shard import shard_bounds
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -200,14 +204,27 @@ def main():
     params = dict(pair_end=1)
     if MIS:
         params["max_mismatch"] = int(MIS)
-    if world > 1:  # leave host cores to the other ranks
-        params["host_threads"] = max(1, (os.cpu_count() or 1) // world)
-    M = capi.Mapper(idx, device=local, **params)
+    # CONTEXTS contexts (one host thread each, the C-ABI's unit of concurrency) share this GPU and split the step's batch:
+    # their H2D / kernels / D2H overlap on separate streams.  Host cores are divided among ranks and contexts.
+    cores = os.cpu_count() or 1
+    params["host_threads"] = max(1, cores // (world * CONTEXTS))
+    mappers = [capi.Mapper(idx, device=local, **params) for _ in range(CONTEXTS)]
+    M = mappers[0]
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    M.set_stream(stream.cuda_stream)   # the library launches on torch's current stream, so torch.cuda.Event brackets its work
     batch = as_batch(*make_pairs(g, PAIRS_PER_GPU, rank))
     n_reads = batch.n
+    bounds = shard_bounds(n_reads, CONTEXTS, True)
+    subs = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        off = batch.offsets[a:b + 1]
+        subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]], (off - off[0]).copy()))
+    pool = ThreadPoolExecutor(CONTEXTS)
+
+    def step(resident):
+        futs = [pool.submit(m.map_reads, sb, resident, False) for m, sb in zip(mappers, subs)]
+        for f in futs:
+            f.result()
 
     def timed(fn, steps):
         barrier()
@@ -223,21 +240,23 @@ def main():
         return float(ms.item())
 
     # ---- device-resident arm ----
-    M.upload_reads(batch)
-    resident = lambda: M.map_reads(batch, resident=True, copy=False)  # noqa: E731
+    for m, sb in zip(mappers, subs):
+        m.upload_reads(sb)
     for _ in range(args.warmup):
-        resident()
+        step(True)
     sampler = ClockSampler(local); sampler.start()
-    ms_res = timed(resident, args.steps)
-    st = M.stats()
+    ms_res = timed(lambda: step(True), args.steps)
+    sts = [m.stats() for m in mappers]
     # ---- end-to-end arm (host buffers in, host results out) ----
-    e2e_fn = lambda: M.map_reads(batch, resident=False, copy=False)  # noqa: E731
-    e2e_fn()
-    ms_e2e = timed(e2e_fn, args.steps)
-    st_e2e = M.stats()
+    step(False)
+    ms_e2e = timed(lambda: step(False), args.steps)
+    sts_e2e = [m.stats() for m in mappers]
     clocks = sampler.result()
+    st = {k: sum(x[k] for x in sts) for k in sts[0]}          # work and kernel time summed over the contexts of this rank
+    st_e2e = {k: sum(x[k] for x in sts_e2e) for k in sts_e2e[0]}
 
-    # kernel-only seeding (no host orchestration, no copies) for the roofline of the dominant kernel
+    # kernel-only seeding over the whole batch on one context (no host orchestration, no copies): roofline of the dominant kernel
+    M.upload_reads(batch)
     M.seed_resident()
     ms_k = []
     for _ in range(max(3, args.steps)):
@@ -255,8 +274,9 @@ def main():
         search_ms = float(np.mean(ms_k))
         achieved = search_bytes / (search_ms * 1e-3) / 1e9
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_ncu.json"))).get("dram_bytes_per_launch")
+        try:   # DRAM bytes of the ncu capture, scaled from its launch (400 k reads) to this launch
+            t = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_ncu.json")))
+            traffic = int(t["dram_bytes_per_launch"] * n_reads / t["reads_in_launch"]) if WORKLOAD == "c2" else None
         except Exception:
             pass
         line = {
@@ -266,7 +286,7 @@ def main():
             "data": "synthetic", "config": workload_config(), "clocks": clocks,
             "e2e": {"value": world * n_reads * args.steps / (ms_e2e * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
-            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+            "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS,
             "roofline": {"bound": "hbm", "kernel": "k_search (FM-index forward extension)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -291,7 +311,8 @@ def main():
             except Exception as ex:  # the baseline is reported, never a reason to lose the measurement
                 line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
         print(json.dumps(line))
-    M.close()
+    for m in mappers:
+        m.close()
     if world > 1:
         dist.destroy_process_group()
 

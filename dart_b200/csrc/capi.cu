@@ -89,13 +89,6 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
     if (bad & 2) throw std::make_pair(DARTGPU_ERR_READ_TOO_LONG, std::string("a read is longer than DARTGPU_MAX_RLEN"));
     const int64_t first = n ? reads->offsets[0] : 0, n_bases = n ? reads->offsets[n] - first : 0;
     c->h_raw.reserve(n_bases + 16); c->h_off.reserve(n + 2);
-    {   // stage the caller's (pageable) buffers into pinned memory with all cores
-        const int64_t chunk = 1 << 20, nchunks = (n_bases + chunk - 1) / chunk;
-#pragma omp parallel for schedule(static) num_threads(threads)
-        for (int64_t k = 0; k < nchunks; k++)
-            memcpy(c->h_raw.p + k * chunk, reads->bases + first + k * chunk, (size_t)std::min(chunk, n_bases - k * chunk));
-        if (n) memcpy(c->h_off.p, reads->offsets, (size_t)(n + 1) * sizeof(int64_t));
-    }
     c->n_reads = n; c->max_rlen = max_rlen;
     c->cap_rec = std::max(1, (max_rlen + 15) / 16);
     c->d_raw.reserve(n_bases + 16); c->d_off.reserve(n + 2); c->d_padded.reserve(n + 2);
@@ -106,8 +99,18 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
     cudaStream_t st = c->stream;
     DG_CUDA(cudaEventRecord(c->ev[0], st));
     if (n) {
-        DG_CUDA(cudaMemcpyAsync(c->d_raw.p, c->h_raw.p, n_bases, cudaMemcpyHostToDevice, st));
+        // The caller's buffers are pageable: stage them through pinned memory in slices, every core copying, and hand
+        // each slice to the DMA engine as soon as it is staged so the host copy of slice k+1 overlaps the transfer of k.
+        memcpy(c->h_off.p, reads->offsets, (size_t)(n + 1) * sizeof(int64_t));
         DG_CUDA(cudaMemcpyAsync(c->d_off.p, c->h_off.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        const int64_t slice = 16 << 20, piece = 1 << 20;
+        for (int64_t s0 = 0; s0 < n_bases; s0 += slice) {
+            const int64_t len = std::min(slice, n_bases - s0), npieces = (len + piece - 1) / piece;
+#pragma omp parallel for schedule(static) num_threads(threads)
+            for (int64_t k = 0; k < npieces; k++)
+                memcpy(c->h_raw.p + s0 + k * piece, reads->bases + first + s0 + k * piece, (size_t)std::min(piece, len - k * piece));
+            DG_CUDA(cudaMemcpyAsync(c->d_raw.p + s0, c->h_raw.p + s0, (size_t)len, cudaMemcpyHostToDevice, st));
+        }
         launch_read_layout(c->d_off.p, n, c->d_rlen.p, c->d_padded.p, st);
         size_t tmp = scan_tmp_bytes(n);
         c->d_scan_tmp.reserve(tmp + 256);
