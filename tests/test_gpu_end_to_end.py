@@ -65,3 +65,34 @@ def test_golden_sam():
         w.update(r1=os.path.join(GOLDEN, r1), r2=os.path.join(GOLDEN, r2) if r2 else None)
         gs, gj = _run_gpu(w, tag="golden_" + tag)
         _compare(gs, os.path.join(GOLDEN, tag + ".sam"), gj, os.path.join(GOLDEN, tag + ".junc"))
+
+
+@pytest.mark.parametrize("cfg,n,extra", [(1, 100_000, ()), (2, 1_000_000, ()), (2, 200_000, ("-mis", "5"))],
+                         ids=["config0-100k-SE", "config1-1M-PE", "config1-200k-PE-mis5"])
+def test_full_size_baseline_configs(cfg, n, extra, tmp_path_factory):
+    """BASELINE.json's own sizes for the two configs that fit a GPU-box call: config[0] (100 k SE x 100 bp) and config[1]
+    (1 M pairs 2x101) on the 4.6 Mbp genome — every SAM record and junctions.tab against the canonical reference."""
+    import hashlib
+    from conftest import WORK, need_ref
+    from dart_b200 import synth
+    from oracle import pyoracle as po
+    need_ref()
+    d = os.path.join(WORK, f"full_c{cfg}_{n}")
+    os.makedirs(d, exist_ok=True)
+    g = synth.config_genome(cfg)
+    fa = os.path.join(d, "genome.fa")
+    if not os.path.exists(os.path.join(d, "idx.bwt")):
+        synth.write_fasta(fa, g)
+        po.build_index(fa, os.path.join(d, "idx"))
+    m1, m2, flags = synth.config_reads(cfg, g, n)
+    synth.write_fastq(os.path.join(d, "r1.fq"), m1, 1 if m2 is not None else None)
+    if m2 is not None:
+        synth.write_fastq(os.path.join(d, "r2.fq"), m2, 2)
+    w = dict(dir=d, idx=os.path.join(d, "idx"), r1=os.path.join(d, "r1.fq"), r2=os.path.join(d, "r2.fq") if m2 is not None else None,
+             flags=flags)
+    rs, rj = run_reference(w, "dart_canon", 1, extra, tag="ref")
+    gs, gj = _run_gpu(w, extra, tag="gpu")
+    md5 = lambda p: hashlib.md5(open(p, "rb").read()).hexdigest()  # noqa: E731
+    if md5(gs) != md5(rs):
+        _compare(gs, rs, gj, rj)          # pinpoints the first differing record
+    assert md5(gj) == md5(rj)
