@@ -136,7 +136,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     c->d_recs.reserve((size_t)n * c->cap_rec);
     c->d_nrec.reserve(n + 1); c->d_nhits.reserve(n + 1); c->d_ncand.reserve(n + 1);
     c->d_seed_off.reserve(n + 2);
-    c->d_big_list.reserve(n + 1); c->d_big_count.reserve(4);
+    c->d_big_list.reserve(n + 1); c->d_big_count.reserve(4); c->d_mid_list.reserve(n + 1); c->d_mid_count.reserve(4);
     size_t tmp = scan_tmp_bytes(n);
     c->d_scan_tmp.reserve(tmp + 256);
 
@@ -144,7 +144,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     a.codes = c->d_codes.p; a.dev_off = c->d_dev_off.p; a.rlen = c->d_rlen.p; a.n_reads = n;
     a.cap_rec = c->cap_rec; a.max_dup = c->prm.max_dup; a.max_gaps = c->prm.max_gaps; a.max_intron = c->prm.max_intron;
     a.recs = c->d_recs.p; a.nrec = c->d_nrec.p; a.nhits = c->d_nhits.p; a.seed_off = c->d_seed_off.p;
-    a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = c->d_big_count.p;
+    a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = c->d_big_count.p; a.mid_list = c->d_mid_list.p; a.mid_count = c->d_mid_count.p;
     a.stats = c->d_stats.p;
 
     DG_CUDA(cudaMemsetAsync(c->d_nhits.p + n, 0, sizeof(uint32_t), st));
@@ -175,7 +175,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     launch_sort_cluster(c->ix, a, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[6], st));
-    c->stats.kernel_launches += (total > 0 ? 2 : 0) + 2;
+    c->stats.kernel_launches += (total > 0 ? 2 : 0) + 3;
 
     if (fetch) {
         c->h_seed_off.reserve(n + 1); c->h_ncand.reserve(n + 1);

@@ -42,7 +42,7 @@ struct dartgpu_ctx {
 
     // ---- seeding buffers ----
     dartgpu::DevBuf<dartgpu::SearchRec> d_recs;
-    dartgpu::DevBuf<uint32_t> d_nrec, d_nhits, d_ncand, d_meta, d_big_list, d_big_count;
+    dartgpu::DevBuf<uint32_t> d_nrec, d_nhits, d_ncand, d_meta, d_big_list, d_big_count, d_mid_list, d_mid_count;
     dartgpu::DevBuf<int64_t> d_seed_off;
     dartgpu::DevBuf<uint64_t> d_keys, d_big_scratch;
     dartgpu::DevBuf<int32_t> d_cand_begin, d_cand_count, d_cand_score;

@@ -105,7 +105,8 @@ struct SeedLaunch {
     int64_t *seed_off;                                          // n_reads+1, exclusive scan of nhits
     uint64_t *keys; uint32_t *meta;                             // per seed slot
     int32_t *cand_begin, *cand_count, *cand_score; uint32_t *ncand;
-    uint32_t *big_list; uint32_t *big_count;                    // reads with more than 32 seeds
+    uint32_t *mid_list; uint32_t *mid_count;                    // reads with 9..32 seeds (one warp each)
+    uint32_t *big_list; uint32_t *big_count;                    // reads with more than 32 seeds (one block each)
     uint64_t *big_scratch; size_t big_scratch_per_cta;          // global sort scratch for reads that exceed smem
     DevStats *stats;
 };

@@ -239,6 +239,9 @@ __global__ void k_expand(SeedLaunch a)
 // ---------------------------------------------------------------------------------------------------
 // kernel 2b: SA locate — bwt_sa / bwt_invPsi (bwt_search.cpp:119-137), one group per hit
 // ---------------------------------------------------------------------------------------------------
+// Hits need 0..sa_intv-1 LF steps each (uniformly spread), so a group that walked one hit per pass would idle half the
+// time waiting for the slowest of the warp's 8 groups (round-1 ncu: 12 of 32 lanes active).  Same cure as in k_search:
+// one loop, one LF step per iteration, a group picks up its next hit the moment it finishes one.
 template <typename IdxT>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_locate(DevIndex ix, SeedLaunch a, int64_t total)
@@ -253,31 +256,44 @@ k_locate(DevIndex ix, SeedLaunch a, int64_t total)
     const char *occq = reinterpret_cast<const char *>(ix.occ + q);
     const int q32 = 32 * q - 1;
     unsigned long long st_lf = 0, st_hits = 0;
-    for (int64_t s = (int64_t)blockIdx.x * GROUPS_PER_CTA + (threadIdx.x >> 2); s < total; s += ngroups) {
-        IdxT k = (IdxT)a.keys[s];
-        uint32_t steps = 0;
-        while (k & sa_mask) {               // one LF step = one block: the symbol at k and its rank come from the same 64 bytes
+    int64_t s = (int64_t)blockIdx.x * GROUPS_PER_CTA + (threadIdx.x >> 2);
+    bool walking = false;
+    IdxT k = 0;
+    uint32_t steps = 0;
+    for (;;) {
+        if (!walking) {
+            if (s >= total) break;
+            k = (IdxT)a.keys[s];
+            steps = 0;
+            walking = true;
+        }
+        if (k & sa_mask) {                  // one LF step = one block: the symbol at k and its rank come from the same 64 bytes
             steps++;
-            if (k == primary) { k = 0; continue; }
-            const IdxT kk = k - (k > primary);
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(kk & ~(IdxT)127) >> 1)));
-            const int o = (int)((uint32_t)kk & 127u);
-            const int c = __shfl_sync(gmask, symbol_at(v.y, o & 31), o >> 5, 4);
-            const uint32_t CH = (c & 2) ? ~0u : 0u, CL = (c & 1) ? ~0u : 0u;
-            uint32_t lo, hi;
-            planes32(v.y, lo, hi);
-            uint32_t eq = (uint32_t)count_eq32(lo, hi, s_mask[max(0, min(32, o - q32))], CH, CL);
-            eq += __shfl_xor_sync(gmask, eq, 1);
-            eq += __shfl_xor_sync(gmask, eq, 2);
-            const IdxT cnt = __shfl_sync(gmask, (IdxT)v.x, c, 4);
-            k = (IdxT)s_L2[c] + cnt + eq;
+            if (k == primary) k = 0;
+            else {
+                const IdxT kk = k - (k > primary);
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(kk & ~(IdxT)127) >> 1)));
+                const int o = (int)((uint32_t)kk & 127u);
+                const int c = __shfl_sync(gmask, symbol_at(v.y, o & 31), o >> 5, 4);
+                const uint32_t CH = (c & 2) ? ~0u : 0u, CL = (c & 1) ? ~0u : 0u;
+                uint32_t lo, hi;
+                planes32(v.y, lo, hi);
+                uint32_t eq = (uint32_t)count_eq32(lo, hi, s_mask[max(0, min(32, o - q32))], CH, CL);
+                eq += __shfl_xor_sync(gmask, eq, 1);
+                eq += __shfl_xor_sync(gmask, eq, 2);
+                const IdxT cnt = __shfl_sync(gmask, (IdxT)v.x, c, 4);
+                k = (IdxT)s_L2[c] + cnt + eq;
+            }
+        } else {
+            const uint64_t g = (uint64_t)steps + __ldg(ix.sa + ((uint64_t)k >> ix.sa_shift));
+            if (q == 0) {
+                const uint32_t m = a.meta[s];
+                a.keys[s] = seed_key(g, m >> 16, m & 0xFFFF);
+            }
+            st_lf += steps; st_hits++;
+            s += ngroups;
+            walking = false;
         }
-        uint64_t g = (uint64_t)steps + __ldg(ix.sa + ((uint64_t)k >> ix.sa_shift));
-        if (q == 0) {
-            uint32_t m = a.meta[s];
-            a.keys[s] = seed_key(g, m >> 16, m & 0xFFFF);
-        }
-        st_lf += steps; st_hits++;
     }
     if (q == 0 && st_hits) {
         atomicAdd(&a.stats->lf_steps, st_lf);
@@ -323,63 +339,91 @@ __device__ __forceinline__ bool chains(const DevIndex &ix, int64_t gj, int rj, i
 
 __device__ __forceinline__ int cand_threshold(int rlen) { return (int)((double)rlen * 0.3); } // AlignmentCandidates.cpp:251
 
+// Sort + cluster one read with a group of W lanes (one seed per lane, n <= W): register bitonic sort of the keys, then the
+// chaining test between neighbours, a segmented sum of the seed lengths and a compaction of the kept clusters — ballots
+// and shuffles only.
+template <int W>
+__device__ __forceinline__ void sort_cluster_group(const DevIndex &ix, const SeedLaunch &a, int r, int64_t off, int n, int gl,
+                                                   unsigned gmask, int gshift)
+{
+    constexpr unsigned WM = W == 32 ? 0xffffffffu : ((1u << (W & 31)) - 1u);
+    uint64_t key = gl < n ? a.keys[off + gl] : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= W; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t other = __shfl_xor_sync(gmask, key, j);
+            bool keep_min = ((gl & j) == 0) == ((gl & k) == 0);
+            key = keep_min ? (key < other ? key : other) : (key > other ? key : other);
+        }
+    }
+    const bool valid = gl < n;
+    if (valid) a.keys[off + gl] = key;
+    const int64_t g = key_gpos(key);
+    const int rp = key_rpos(key), len = key_len(key);
+    const int64_t pd = g - rp;
+    const unsigned nonneg = (__ballot_sync(gmask, valid && pd >= 0) >> gshift) & WM;
+    const int first = nonneg ? __ffs(nonneg) - 1 : n;
+    const int64_t gprev = __shfl_up_sync(gmask, g, 1, W);
+    const int rprev = __shfl_up_sync(gmask, rp, 1, W);
+    const bool in = valid && gl >= first;
+    const bool chain = in && gl > first && chains(ix, gprev, rprev, g, rp, a.max_gaps, a.max_intron);
+    const bool head = in && !chain;
+    int v = in ? len : 0;
+#pragma unroll
+    for (int d = 1; d < W; d <<= 1) { int t = __shfl_up_sync(gmask, v, d, W); if (gl >= d) v += t; }
+    const unsigned heads = (__ballot_sync(gmask, head) >> gshift) & WM;
+    const unsigned higher = gl == W - 1 ? 0u : (heads & ~((2u << gl) - 1u));
+    const int nh = higher ? __ffs(higher) - 1 : n;
+    const int last = min(max(nh - 1, 0), W - 1);
+    const int pend = __shfl_sync(gmask, v, last, W);
+    int pprev = __shfl_up_sync(gmask, v, 1, W);
+    if (gl == 0) pprev = 0;
+    const int score = pend - pprev;
+    const bool keep = head && score > cand_threshold(a.rlen[r]);
+    const unsigned km = (__ballot_sync(gmask, keep) >> gshift) & WM;
+    if (keep) {
+        const int ci = __popc(km & ((1u << gl) - 1u));
+        a.cand_begin[off + ci] = gl;
+        a.cand_count[off + ci] = nh - gl;
+        a.cand_score[off + ci] = score;
+    }
+    if (gl == 0) a.ncand[r] = __popc(km);
+}
+
+// first pass: 8 lanes per read (most reads have 1-6 seeds); reads with more are queued for wider groups
+__global__ void __launch_bounds__(256)
+k_sort_cluster_small(DevIndex ix, SeedLaunch a)
+{
+    const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & ~7;
+    const unsigned gmask = 0xFFu << gshift;
+    const int ngroups = (gridDim.x * blockDim.x) >> 3;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < a.n_reads; r += ngroups) {
+        const int64_t off = a.seed_off[r];
+        const int64_t n64 = a.seed_off[r + 1] - off;
+        if (n64 == 0) { if (gl == 0) a.ncand[r] = 0; continue; }
+        if (n64 > 8) {
+            if (gl == 0) {
+                if (n64 > 32) { uint32_t i = atomicAdd(a.big_count, 1u); a.big_list[i] = (uint32_t)r; }
+                else { uint32_t i = atomicAdd(a.mid_count, 1u); a.mid_list[i] = (uint32_t)r; }
+            }
+            continue;
+        }
+        sort_cluster_group<8>(ix, a, r, off, (int)n64, gl, gmask, gshift);
+    }
+}
+
+// second pass: one warp per queued read with 9..32 seeds
 __global__ void __launch_bounds__(256)
 k_sort_cluster_warp(DevIndex ix, SeedLaunch a)
 {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
-        int64_t off = a.seed_off[r];
-        int64_t n64 = a.seed_off[r + 1] - off;
-        if (n64 == 0) { if (lane == 0) a.ncand[r] = 0; continue; }
-        if (n64 > 32) {
-            if (lane == 0) { uint32_t i = atomicAdd(a.big_count, 1u); a.big_list[i] = (uint32_t)r; }
-            continue;
-        }
-        int n = (int)n64;
-        uint64_t key = lane < n ? a.keys[off + lane] : ~0ull;
-        // bitonic sort across the warp, ascending
-#pragma unroll
-        for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                uint64_t other = __shfl_xor_sync(FULL, key, j);
-                bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
-                key = keep_min ? (key < other ? key : other) : (key > other ? key : other);
-            }
-        }
-        bool valid = lane < n;
-        if (valid) a.keys[off + lane] = key;
-        int64_t g = key_gpos(key);
-        int rp = key_rpos(key), len = key_len(key);
-        int64_t pd = g - rp;
-        unsigned nonneg = __ballot_sync(FULL, valid && pd >= 0);
-        int first = nonneg ? __ffs(nonneg) - 1 : n;
-        int64_t gprev = __shfl_up_sync(FULL, g, 1);
-        int rprev = __shfl_up_sync(FULL, rp, 1);
-        bool in = valid && lane >= first;
-        bool chain = in && lane > first && chains(ix, gprev, rprev, g, rp, a.max_gaps, a.max_intron);
-        bool head = in && !chain;
-        int v = in ? len : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, v, d); if (lane >= d) v += t; }
-        unsigned heads = __ballot_sync(FULL, head);
-        unsigned higher = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-        int nh = higher ? __ffs(higher) - 1 : n;
-        int last = min(max(nh - 1, 0), 31);
-        int pend = __shfl_sync(FULL, v, last);
-        int pprev = __shfl_up_sync(FULL, v, 1);
-        if (lane == 0) pprev = 0;
-        int score = pend - pprev;
-        bool keep = head && score > cand_threshold(a.rlen[r]);
-        unsigned km = __ballot_sync(FULL, keep);
-        if (keep) {
-            int ci = __popc(km & ((1u << lane) - 1u));
-            a.cand_begin[off + ci] = lane;
-            a.cand_count[off + ci] = nh - lane;
-            a.cand_score[off + ci] = score;
-        }
-        if (lane == 0) a.ncand[r] = __popc(km);
+    const uint32_t nmid = *a.mid_count;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nmid; w += nwarps) {
+        const int r = (int)a.mid_list[w];
+        const int64_t off = a.seed_off[r];
+        sort_cluster_group<32>(ix, a, r, off, (int)(a.seed_off[r + 1] - off), lane, FULL, 0);
     }
 }
 
@@ -449,9 +493,11 @@ void launch_sort_cluster(const DevIndex &ix, const SeedLaunch &a, cudaStream_t s
 {
     if (a.n_reads <= 0) return;
     cudaMemsetAsync(a.big_count, 0, sizeof(uint32_t), st);
-    int64_t want = ((int64_t)a.n_reads * 32 + 255) / 256;
+    cudaMemsetAsync(a.mid_count, 0, sizeof(uint32_t), st);
+    int64_t want = ((int64_t)a.n_reads * 8 + 255) / 256;
     int grid = (int)(want < 148 * 8 ? want : 148 * 8);
-    k_sort_cluster_warp<<<grid, 256, 0, st>>>(ix, a);
+    k_sort_cluster_small<<<grid, 256, 0, st>>>(ix, a);
+    k_sort_cluster_warp<<<148 * 4, 256, 0, st>>>(ix, a);
     k_sort_cluster_big<<<148, 256, 0, st>>>(ix, a);
 }
 
