@@ -19,6 +19,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <algorithm>
+
 #include "dartgpu_internal.h"
 #include "rank.cuh"
 
@@ -91,11 +93,18 @@ k_search(DevIndex ix, SeedLaunch a)
     stage_tables(ix, s_L2, s_mask);
     uint32_t *pk = s_pk[grp];
     uint16_t *am = s_am[grp];
-    const int stride = gridDim.x * GROUPS_PER_CTA;
     const IdxT primary = (IdxT)ix.primary;
     const char *occq = reinterpret_cast<const char *>(ix.occ + q);   // this lane's quarter of block 0
     const int q32 = 32 * q - 1;
-    int r = blockIdx.x * GROUPS_PER_CTA + grp;
+    // Reads are handed out dynamically: the CTA owns a contiguous range and its 32 groups draw the next read from a
+    // shared counter when they finish one (round-1 ncu: with a static stride a quarter of the lanes idled in the step
+    // waiting for the warp's slowest group).  Results are indexed by read, so the order does not matter.
+    __shared__ int s_next;
+    const int per_cta = (a.n_reads + gridDim.x - 1) / gridDim.x;
+    const int r_end = min(a.n_reads, (int)(blockIdx.x + 1) * per_cta);
+    if (threadIdx.x == 0) s_next = blockIdx.x * per_cta;
+    __syncthreads();
+    int r = 0;
 
     bool have_read = false, searching = false;
     int rl = 0, start = 0, p = 0, cw = -1;
@@ -108,7 +117,9 @@ k_search(DevIndex ix, SeedLaunch a)
             bool done = false;
             for (;;) {
                 if (!have_read) {
-                    if (r >= a.n_reads) { done = true; break; }
+                    if (q == 0) r = atomicAdd(&s_next, 1);
+                    r = __shfl_sync(gmask, r, 0, 4);
+                    if (r >= r_end) { done = true; break; }
                     rl = a.rlen[r];
                     stage_read(a.codes, a.dev_off[r], rl, pk, am, q, gmask);
                     start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
@@ -117,7 +128,6 @@ k_search(DevIndex ix, SeedLaunch a)
                 if (start < rl - 13) break;
                 if (q == 0) { a.nrec[r] = nr; a.nhits[r] = nh; }
                 have_read = false;
-                r += stride;
             }
             if (done) break;
             int c0 = (pk[start >> 4] >> ((start & 15) * 2)) & 3;
@@ -189,9 +199,20 @@ static bool fits32(const DevIndex &ix) { return !ix.force64 && ix.seq_len + 2 < 
 void launch_search(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
 {
     if (a.n_reads <= 0) return;
+    // exactly one wave: as many CTAs as are resident at once (a partial second wave would idle most SMs at the end)
+    static int occ32 = 0, occ64 = 0, sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k_search<uint32_t>, SEARCH_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_search<uint64_t>, SEARCH_THREADS, 0);
+    }
+    const bool narrow = fits32(ix);
     int want = (a.n_reads + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
-    int grid = want < 148 * 16 ? want : 148 * 16; // 16 CTAs of 128 threads fill an SM's 2048 thread slots
-    if (fits32(ix)) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
+    int grid = sms * std::max(1, narrow ? occ32 : occ64);
+    if (want < grid) grid = want;
+    if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
     else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
 }
 
