@@ -34,8 +34,8 @@ struct DevIndex {
     int force64;             // tests only (DARTGPU_FORCE_IDX64=1): run the 64-bit interval kernels on a small index
 };
 
-struct SearchRec {           // one qualifying BWT_Search result: SA interval still to be located
-    uint64_t x0;
+struct SearchRec {           // one qualifying BWT_Search result: SA interval (of the reverse-complemented match) still to be located
+    uint64_t sa_begin;
     uint32_t freq;
     uint16_t start, len;
 };

@@ -13,8 +13,9 @@
 //     single loop whose every iteration performs exactly one rank step, so the 8 groups of a warp stay
 //     converged although their reads, search starts and match lengths differ.
 //   * reads are staged in shared memory 2-bit packed (+ a 1-bit "not ACGT" plane).
-//   * search only records SA intervals; after a prefix sum over the hit counts a second kernel resolves
-//     every hit with its own group (LF walk to the next SA sample), so repetitive reads do not serialise.
+//   * search only records SA intervals (of the reverse-complemented pattern, see k_search); after a prefix sum over
+//     the hit counts a second kernel resolves every hit with its own group (LF walk to the next SA sample, then the
+//     mirror p -> 2G - p - len), so repetitive reads do not serialise.
 //   * seeds are 64-bit keys (gPos | rPos | len): sorting the keys is the reference's CompByGenomePos order.
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -61,15 +62,20 @@ __device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, in
 // ---------------------------------------------------------------------------------------------------
 // kernel 1: maximal exact-match segment search (IdentifySeedPairs' loop around BWT_Search, without locate)
 //
-// One forward-extension step per loop iteration (bwt_2occ4 + interval update, bwt_search.cpp:152-170), restated so
-// that a lane never needs more than two popcounts per block:
-//     n2   = Occ(c,l) - Occ(c,k)                       size of the new interval
-//     x1'  = L2[c] + 1 + Occ(c,k)                      its start on the reverse-complement strand
-//     x0'  = x0 + [sentinel in range] + sum_{j>c} (Occ(j,l) - Occ(j,k))      its start on the forward strand
-// Occ(j,.) = block header count (lane j holds it) + in-block count; the in-block parts of the 4 lanes are summed as
-// four 8-bit fields of one word (two xor-shuffles), the header differences travel as 32-bit values (interval widths
-// are < 2^32, checked at index load).  IdxT = uint32_t when the whole text fits 32 bits (every tested genome and
-// BASELINE configs 1, 2, 5), uint64_t otherwise (3.1 Gbp: 2G = 6.2e9) — same code, narrower interval arithmetic.
+// One forward-extension step per loop iteration (bwt_2occ4 + interval update, bwt_search.cpp:152-170).  The reference
+// carries the bi-interval (x0 = SA interval of the pattern P, x1 = SA interval of revcomp(P), x2 = size) and locates from
+// x0.  Because the text is its own reverse complement (forward strand followed by the reverse-complement strand), the
+// occurrences of revcomp(P) are the occurrences of P mirrored: p -> 2G - p - |P|.  The seeds are sorted by (gPos,rPos)
+// right after (IdentifySeedPairs), so locating from x1 and mirroring yields the identical seed list — and extending P
+// forward by base b is then a plain backward step of revcomp(P) with c = 3 - b:
+//     n2   = Occ(c,l) - Occ(c,k)          size of the new interval          (k = x1-1, l = x1-1+x2)
+//     x1'  = L2[c] + 1 + Occ(c,k)         its start
+// i.e. one "equal to c" popcount per block and no forward-interval bookkeeping at all (round-1 ncu: the kernel is bound
+// by the integer pipes, not by memory; dropping x0 removes ~30 % of the step's instructions).
+// Occ(c,.) = block header count (lane c holds it) + in-block count; the in-block parts of the 4 lanes are summed as two
+// 8-bit fields of one word (two xor-shuffles), the header difference travels as a 32-bit value (interval widths are
+// < 2^32, checked at index load).  IdxT = uint32_t when the whole text fits 32 bits (every tested genome and BASELINE
+// configs 1, 2, 5), uint64_t otherwise (3.1 Gbp: 2G = 6.2e9) — same code, narrower interval arithmetic.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_tables(const DevIndex &ix, uint64_t *s_L2, uint32_t *s_mask)
 {
@@ -109,7 +115,7 @@ k_search(DevIndex ix, SeedLaunch a)
     bool have_read = false, searching = false;
     int rl = 0, start = 0, p = 0, cw = -1;
     uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0;
-    IdxT x0 = 0, x1 = 0;
+    IdxT x1 = 0;
     uint32_t st_steps = 0, st_splits = 0;
 
     for (;;) {
@@ -131,7 +137,7 @@ k_search(DevIndex ix, SeedLaunch a)
             }
             if (done) break;
             int c0 = (pk[start >> 4] >> ((start & 15) * 2)) & 3;
-            x0 = (IdxT)s_L2[c0] + 1; x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
+            x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
             p = start + 1;
             searching = true;
         }
@@ -151,25 +157,19 @@ k_search(DevIndex ix, SeedLaunch a)
             const uint32_t CH = (code & 2u) ? 0u : ~0u, CL = (code & 1u) ? 0u : ~0u;
             st_steps++; st_splits += (uint32_t)((kk ^ ll) >> 7 != 0);
             uint32_t lo, hi;
-            int eqk, gtk, eql, gtl;
             planes32(vk.y, lo, hi);
-            count_eq_gt32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)kk & 127u) - q32))], CH, CL, eqk, gtk);
+            const int eqk = count_eq32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)kk & 127u) - q32))], CH, CL);
             planes32(vl.y, lo, hi);
-            count_eq_gt32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)ll & 127u) - q32))], CH, CL, eql, gtl);
-            uint32_t pc = (uint32_t)eqk | (uint32_t)gtk << 8 | (uint32_t)eql << 16 | (uint32_t)gtl << 24;
+            const int eql = count_eq32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)ll & 127u) - q32))], CH, CL);
+            uint32_t pc = (uint32_t)eqk | (uint32_t)eql << 16;
             pc += __shfl_xor_sync(gmask, pc, 1);
             pc += __shfl_xor_sync(gmask, pc, 2);
-            const uint32_t D = (uint32_t)vl.x - (uint32_t)vk.x;
-            const uint32_t Dc = __shfl_sync(gmask, D, c, 4);
-            uint32_t Dab = q > c ? D : 0u;
-            Dab += __shfl_xor_sync(gmask, Dab, 1);
-            Dab += __shfl_xor_sync(gmask, Dab, 2);
+            const uint32_t Dc = __shfl_sync(gmask, (uint32_t)vl.x - (uint32_t)vk.x, c, 4);
             const IdxT cntk = __shfl_sync(gmask, (IdxT)vk.x, c, 4);
-            const uint32_t EK = pc & 0xffu, GK = (pc >> 8) & 0xffu, EL = (pc >> 16) & 0xffu, GL = pc >> 24;
+            const uint32_t EK = pc & 0xffffu, EL = pc >> 16;
             const uint32_t n2 = Dc + EL - EK;
             if (n2 == 0) end = true;
             else {
-                x0 += (IdxT)(((x1 <= primary && (IdxT)(x1 + x2 - 1) >= primary) ? 1u : 0u) + (uint32_t)(Dab + GL - GK));
                 x1 = (IdxT)s_L2[c] + 1 + cntk + EK;
                 x2 = n2;
                 p++;
@@ -179,7 +179,7 @@ k_search(DevIndex ix, SeedLaunch a)
             int len = p - start;
             if (x2 <= a.max_dup && len >= 16) { // bwt_search.cpp:173
                 if (q == 0 && (int)nr < a.cap_rec) {
-                    SearchRec rec; rec.x0 = x0; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
+                    SearchRec rec; rec.sa_begin = x1; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
                     a.recs[(int64_t)r * a.cap_rec + nr] = rec;
                 }
                 nr++; nh += x2;
@@ -252,7 +252,7 @@ __global__ void k_expand(SeedLaunch a)
         for (int i = 0; i < nr; i++) {
             SearchRec rec = a.recs[(int64_t)r * a.cap_rec + i];
             uint32_t m = (uint32_t)rec.start << 16 | rec.len;
-            for (uint32_t j = 0; j < rec.freq; j++, o++) { a.keys[o] = rec.x0 + j; a.meta[o] = m; }
+            for (uint32_t j = 0; j < rec.freq; j++, o++) { a.keys[o] = rec.sa_begin + j; a.meta[o] = m; }
         }
     }
 }
@@ -306,10 +306,11 @@ k_locate(DevIndex ix, SeedLaunch a, int64_t total)
                 k = (IdxT)s_L2[c] + cnt + eq;
             }
         } else {
-            const uint64_t g = (uint64_t)steps + __ldg(ix.sa + ((uint64_t)k >> ix.sa_shift));
+            // position of revcomp(P) on the text; P itself starts at the mirrored coordinate 2G - p' - |P|
+            const uint64_t prc = (uint64_t)steps + __ldg(ix.sa + ((uint64_t)k >> ix.sa_shift));
             if (q == 0) {
                 const uint32_t m = a.meta[s];
-                a.keys[s] = seed_key(g, m >> 16, m & 0xFFFF);
+                a.keys[s] = seed_key(2 * (uint64_t)ix.G - prc - (m & 0xFFFF), m >> 16, m & 0xFFFF);
             }
             st_lf += steps; st_hits++;
             s += ngroups;

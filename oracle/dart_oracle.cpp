@@ -146,19 +146,22 @@ extern "C" uint64_t or_locate(or_index *ix, uint64_t k)
     return steps + ix->sa[k / ix->sa_intv];
 }
 
-// BWT_Search (/root/reference/src/bwt_search.cpp:139-182)
-extern "C" int or_search(or_index *ix, const uint8_t *s, int start, int stop, int max_dup,
-                         int *len_out, uint64_t *locs, int cap)
+// BWT_Search (/root/reference/src/bwt_search.cpp:139-182).  mirrored = false: locate from the forward interval as the
+// reference does.  mirrored = true: locate from the reverse-complement interval and mirror (the CUDA path's route).
+static int search_impl(or_index *ix, const uint8_t *s, int start, int stop, int max_dup, int *len_out, uint64_t *locs, int cap,
+                       bool mirrored, bool count)
 {
-    ix->ctr.searches++;
+    if (count) ix->ctr.searches++;
     int c0 = s[start];
     uint64_t x0 = ix->L2[c0] + 1, x1 = ix->L2[3 - c0] + 1, x2 = ix->L2[c0 + 1] - ix->L2[c0];
     int pos;
     for (pos = start + 1; pos < stop; pos++) {
         if (s[pos] > 3) break;
         uint64_t k = x1 - 1, l = x1 - 1 + x2, tk[4], tl[4];
-        ix->ctr.ext_steps++;
-        ix->ctr.ext_blocks += ((k - (k >= ix->primary)) >> 7) == ((l - (l >= ix->primary)) >> 7) ? 1 : 2;
+        if (count) {
+            ix->ctr.ext_steps++;
+            ix->ctr.ext_blocks += ((k - (k >= ix->primary)) >> 7) == ((l - (l >= ix->primary)) >> 7) ? 1 : 2;
+        }
         or_rank4(ix, k, tk);
         or_rank4(ix, l, tl);
         int c = 3 - s[pos];
@@ -172,12 +175,36 @@ extern "C" int or_search(or_index *ix, const uint8_t *s, int start, int stop, in
     *len_out = 0;
     if (x2 <= (uint64_t)(unsigned)max_dup && (*len_out = pos - start) >= 16) {
         for (uint64_t j = 0; j < x2; j++) {
-            uint64_t g = or_locate(ix, x0 + j);
+            uint64_t g;
+            if (!mirrored) {
+                g = or_locate(ix, x0 + j);
+                if (count) {   // the walk the CUDA path does for the same hit, counted without touching the other counters
+                    or_counters keep = ix->ctr;
+                    or_locate(ix, x1 + j);
+                    uint64_t walked = ix->ctr.lf_steps - keep.lf_steps;
+                    ix->ctr = keep;
+                    ix->ctr.lf_steps_rc += walked;
+                }
+            } else {
+                or_counters keep = ix->ctr;
+                g = 2 * (uint64_t)ix->G - or_locate(ix, x1 + j) - (uint64_t)*len_out;
+                ix->ctr = keep;
+            }
             if ((int)j < cap) locs[j] = g;
         }
         return (int)x2;
     }
     return 0;
+}
+
+extern "C" int or_search(or_index *ix, const uint8_t *s, int start, int stop, int max_dup, int *len_out, uint64_t *locs, int cap)
+{
+    return search_impl(ix, s, start, stop, max_dup, len_out, locs, cap, false, true);
+}
+
+extern "C" int or_search_mirrored(or_index *ix, const uint8_t *s, int start, int stop, int max_dup, int *len_out, uint64_t *locs, int cap)
+{
+    return search_impl(ix, s, start, stop, max_dup, len_out, locs, cap, true, false);
 }
 
 // IdentifySeedPairs (/root/reference/src/AlignmentCandidates.cpp:181-215)

@@ -40,6 +40,7 @@ typedef struct {
     uint64_t read_bases;    /* bases of reads seeded                              */
     uint64_t nw_calls, nw_cells;
     uint64_t kmer_calls, kmer_window_bases, kmer_read_bases;
+    uint64_t lf_steps_rc;   /* LF steps when the same hits are located from the reverse-complement interval (what the CUDA path walks) */
 } or_counters;
 
 or_index *or_load(const char *prefix);           /* <prefix>.bwt .sa .pac .ann */
@@ -57,6 +58,10 @@ uint64_t  or_locate(or_index *, uint64_t k);                         /* bwt_sa  
 /* BWT_Search: returns freq, *len = match length (0 when too repetitive); locs in SA order */
 int or_search(or_index *, const uint8_t *codes, int start, int stop, int max_dup,
               int *len, uint64_t *locs, int cap);
+/* The same search located from the other half of the bi-interval: positions of revcomp(match), mirrored back with
+ * p -> 2G - p - len.  Must be the same set as or_search's locs (the text is its own reverse complement). */
+int or_search_mirrored(or_index *, const uint8_t *codes, int start, int stop, int max_dup,
+                       int *len, uint64_t *locs, int cap);
 /* IdentifySeedPairs: seeds sorted by (gPos,rPos). Returns count (may exceed cap; only cap are written) */
 int or_seed_read(or_index *, const uint8_t *codes, int rlen, int max_dup,
                  int32_t *rpos, int64_t *gpos, int32_t *len, int cap);

@@ -55,7 +55,7 @@ _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "searches", "ext_steps", "ext_blocks", "lf_steps", "hits", "seeds", "read_bases",
-        "nw_calls", "nw_cells", "kmer_calls", "kmer_window_bases", "kmer_read_bases")]
+        "nw_calls", "nw_cells", "kmer_calls", "kmer_window_bases", "kmer_read_bases", "lf_steps_rc")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -79,6 +79,7 @@ class Oracle:
         L.or_locate.restype = C.c_uint64
         L.or_locate.argtypes = [C.c_void_p, C.c_uint64]
         L.or_search.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _u64p, C.c_int]
+        L.or_search_mirrored.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _u64p, C.c_int]
         L.or_seed_read.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _i32p, _i64p, _i32p, C.c_int]
         L.or_cluster_read.argtypes = [C.c_void_p, C.c_int, C.c_int, _i32p, _i64p, _i32p, C.c_int, C.c_int,
                                       _i32p, _i32p, _i32p, C.c_int]
@@ -121,6 +122,12 @@ class Oracle:
         ln = C.c_int(0)
         locs = np.zeros(max(max_dup, 1), dtype=np.uint64)
         f = self.L.or_search(self.h, np.ascontiguousarray(codes, np.uint8), start, stop, max_dup, C.byref(ln), locs, len(locs))
+        return ln.value, f, locs[:f].copy()
+
+    def search_mirrored(self, codes: np.ndarray, start: int, stop: int, max_dup: int = 100):
+        ln = C.c_int(0)
+        locs = np.zeros(max(max_dup, 1), dtype=np.uint64)
+        f = self.L.or_search_mirrored(self.h, np.ascontiguousarray(codes, np.uint8), start, stop, max_dup, C.byref(ln), locs, len(locs))
         return ln.value, f, locs[:f].copy()
 
     def seeds(self, codes: np.ndarray, max_dup: int = 100, cap: int = 1 << 16):

@@ -1,5 +1,6 @@
 """Pin the CPU oracle against the UNMODIFIED reference (oracle/_ref/libdartref.so), stage by stage, on freshly
 generated workloads. One index per process (the reference keeps it in globals), so everything runs on c3."""
+import os
 import random
 
 import numpy as np
@@ -49,6 +50,38 @@ def test_search_seeds_candidates(pair):
         assert (cs == rs).all() and (cc == rn).all()
         flat = np.concatenate([np.arange(b, b + n) for b, n in zip(cb, cc)]) if len(cb) else np.zeros(0, int)
         assert (r1[flat] == sr).all() and (g1[flat] == sg).all()
+
+
+def test_mirrored_locate_gives_the_reference_hits():
+    """The CUDA path locates each match from the reverse-complement half of the bi-interval and mirrors the coordinate
+    (p -> 2G - p - len).  The text is its own reverse complement, so the hit SET must equal the reference's LocArr —
+    checked here against the reference itself on a repeat-rich index with -max_dup 10000, every search start of many reads."""
+    import subprocess, sys, json
+    from conftest import ROOT
+    code = """
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+from oracle import pyoracle as po
+from conftest import workload, read_fastq_seqs
+w = workload("c5")
+O, R = po.Oracle(w["idx"]), po.Reference(w["idx"])
+R.set_params(max_dup=10000)
+n = multi = 0
+for s in read_fastq_seqs(w["r1"], 400) + [b"ACACACACACACACACACACACACACACACACACACACAC", b"A" * 60]:
+    c = po.encode(s)
+    for start in range(0, max(1, len(c) - 14), 3):
+        if c[start] > 3: continue
+        lr, fr, xr = R.search(c, start, len(c))
+        lm, fm, xm = O.search_mirrored(c, start, len(c), max_dup=10000)
+        assert (lr, fr) == (lm, fm), (s, start)
+        assert sorted(xr.tolist()) == sorted(xm.tolist()), (s, start)
+        n += 1; multi += fr > 1
+print(json.dumps([n, multi]))
+""" % os.path.join(ROOT, "tests")
+    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, cwd=os.path.join(ROOT, "tests"),
+                         env=dict(os.environ, PYTHONPATH=ROOT)).stdout.decode().strip().splitlines()[-1]
+    n, multi = json.loads(out)
+    assert n > 5000 and multi > 100
 
 
 def _rnd(rng, n):
