@@ -49,6 +49,7 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
     uint32_t *cnt = tab + tab_cap;              // ring of per-diagonal aggregates
     uint32_t *rmin = cnt + ring, *rmax = rmin + ring;
     uint32_t *bal = rmax + ring;                // occupancy bitmaps of the diagonals being retired
+    uint32_t *bm = bal + ring / 32 + 8;          // 64 Kbit presence bitmap of the read gap's 8-mer ids
     __shared__ int s_nk, s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -119,6 +120,9 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                         __syncthreads();
                     }
                 for (int s = tid; s < ring; s += KMER_THREADS) { cnt[s] = 0; rmin[s] = 0xFFFFFFFFu; rmax[s] = 0; }
+                for (int s = tid; s < 2048; s += KMER_THREADS) bm[s] = 0;
+                __syncthreads();
+                for (int i = tid; i < nk; i += KMER_THREADS) { const uint32_t w = tab[i] >> 16; atomicOr(&bm[w >> 5], 1u << (w & 31)); }
                 __syncthreads();
 
                 // ---- 2. stream the window KMER_TILE positions at a time; retire diagonals in increasing PosDiff order ----
@@ -126,33 +130,28 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
                 const int dd_end = (ngk - 1) + L1 + 1; // one past the largest diagonal index (dd = gPos - rPos + L1)
                 int s_acc = 1, max_len = 0;             // live in warp 0 only
                 int fin = 8;
-                int steps = 0;
-                for (int t = nk; t > 0; t >>= 1) steps++;       // iterations of a lower_bound over nk entries
                 for (int g0 = 0; g0 < ngk; g0 += KMER_TILE) {
-                    // four positions per thread: all eight reference words are in flight before the first lookup
+                    // four positions per thread: all eight reference words are in flight before the first lookup.  A 64 Kbit
+                    // presence bitmap of the read gap's 8-mers rejects almost every window position with one shared-memory
+                    // load (round-1 ncu: binary-searching every position was half of the kernel's instructions).
                     uint32_t wid[KMER_PPT];
-                    int lo[KMER_PPT], hi[KMER_PPT];
 #pragma unroll
                     for (int i = 0; i < KMER_PPT; i++) {
                         const int g = g0 + tid + KMER_THREADS * i;
-                        wid[i] = g < ngk ? genome_kmer(ix, J.gpos + g) : 0u;
-                        lo[i] = 0; hi[i] = g < ngk ? nk : 0;
+                        wid[i] = g < ngk ? genome_kmer(ix, J.gpos + g) : 0xFFFFFFFFu;
                     }
-                    for (int it = 0; it < steps; it++) {
 #pragma unroll
-                        for (int i = 0; i < KMER_PPT; i++) {
-                            if (lo[i] < hi[i]) { int mid = (lo[i] + hi[i]) >> 1; if (tab[mid] < (wid[i] << 16)) lo[i] = mid + 1; else hi[i] = mid; }
+                    for (int i = 0; i < KMER_PPT; i++) {
+                        const uint32_t w = wid[i];
+                        if (w == 0xFFFFFFFFu || !((bm[w >> 5] >> (w & 31)) & 1u)) continue;
+                        const int g = g0 + tid + KMER_THREADS * i;
+                        int lo = 0, hi = nk;
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (tab[mid] < (w << 16)) lo = mid + 1; else hi = mid; }
+                        for (int e = lo; e < nk && (tab[e] >> 16) == w; e++) {
+                            const uint32_t r = tab[e] & 0xFFFFu;
+                            const int slot = (g - (int)r + L1) & (ring - 1);
+                            atomicAdd(&cnt[slot], 1u); atomicMin(&rmin[slot], r); atomicMax(&rmax[slot], r);
                         }
-                    }
-#pragma unroll
-                    for (int i = 0; i < KMER_PPT; i++) {
-                        const int g = g0 + tid + KMER_THREADS * i;
-                        if (g < ngk)
-                            for (int e = lo[i]; e < nk && (tab[e] >> 16) == wid[i]; e++) {
-                                const uint32_t r = tab[e] & 0xFFFFu;
-                                const int slot = (g - (int)r + L1) & (ring - 1);
-                                atomicAdd(&cnt[slot], 1u); atomicMin(&rmin[slot], r); atomicMax(&rmax[slot], r);
-                            }
                     }
                     __syncthreads();
                     const bool last_tile = g0 + KMER_TILE >= ngk;
@@ -207,7 +206,7 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
     if (n_jobs <= 0) return;
     int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
     int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
-    size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8) * 4;
+    size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8 + 2048) * 4;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
