@@ -85,7 +85,7 @@ __device__ __forceinline__ void stage_tables(const DevIndex &ix, uint64_t *s_L2,
 }
 
 template <typename IdxT>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+__global__ void __launch_bounds__(SEARCH_THREADS, 16)
 k_search(DevIndex ix, SeedLaunch a)
 {
     __shared__ uint32_t s_pk[GROUPS_PER_CTA][RWORDS];
