@@ -45,10 +45,11 @@ def prepare_genome():
     """Config-1/2 genome (4.6 Mbp, seed 1001) + the reference's own index builder. Input preparation, not timed."""
     from dart_b200 import synth
     os.makedirs(WORK, exist_ok=True)
-    idx = os.path.join(WORK, "idx" if WORKLOAD == "c2" else f"idx_c3_{SCALE}")
-    g = synth.config_genome(2) if WORKLOAD == "c2" else synth.config_genome(3, SCALE)
+    idx = os.path.join(WORK, "idx" if WORKLOAD == "c2" else f"idx_{'c5' if WORKLOAD == 'c5' else 'c3'}_{SCALE}")
+    g = (synth.config_genome(2) if WORKLOAD == "c2" else synth.config_genome(5, SCALE) if WORKLOAD == "c5"
+         else synth.config_genome(3, SCALE))
     if not all(os.path.exists(idx + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
-        fa = os.path.join(WORK, "genome.fa" if WORKLOAD == "c2" else "genome_c3.fa")
+        fa = os.path.join(WORK, "genome.fa" if WORKLOAD == "c2" else f"genome_{WORKLOAD}.fa")
         synth.write_fasta(fa, g)
         builder = os.path.join(ROOT, "oracle", "_ref", "bwt_index")
         if not os.path.exists(builder):
@@ -63,6 +64,11 @@ def make_pairs(g, n_pairs, rank):
     from dart_b200 import synth
     if WORKLOAD == "c2":
         return synth.simulate_pairs(g, n_pairs, READ_LEN, 0.01, seed=2002 + rank)
+    if WORKLOAD == "c4":   # config[3]: 2x250, 3 % substitutions + 1-3 bp indels, -mis 10
+        return synth.simulate_pairs(g, n_pairs, 250, 0.03, seed=2004 + rank, frag_mean=600, frag_sd=50, frag_min=500, frag_max=900,
+                                    p_ins=0.002, p_del=0.002)
+    if WORKLOAD == "c5":   # config[4]: repeat-rich genome, -m -max_dup 10000 -all_sj
+        return synth.simulate_pairs(g, n_pairs, READ_LEN, 0.01, seed=2005 + rank)
     return synth.simulate_pairs(g, n_pairs, READ_LEN, 0.01, seed=2003 + rank, spliced=True, frag_min=202, frag_max=500)
 
 
@@ -138,7 +144,7 @@ def run_reference_arm(args, rank):
         return
     g, idx = prepare_genome()
     cores = os.cpu_count() or 1
-    extra = ["-mis", MIS] if MIS else []
+    extra = (["-mis", MIS] if MIS else []) + (["-m", "-max_dup", "10000", "-all_sj"] if WORKLOAD == "c5" else [])
     r1, r2, e1, e2 = reference_setup(g, idx, REF_SAMPLE_PAIRS)
     load = min(time_reference(idx, e1, e2, 2, cores, extra) for _ in range(2))
     for _ in range(args.warmup):
@@ -160,8 +166,10 @@ def run_reference_arm(args, rank):
 def workload_config(sample_pairs=None):
     wl = ("BASELINE config[1]: synthetic 4.6 Mbp random genome (seed 1001), paired-end 2x101 bp, 1% substitutions, FR fragments ~N(300,30)"
           if WORKLOAD == "c2" else
+          f"BASELINE config[4] scaled x{SCALE}: repeat-rich {4.6 * SCALE:.1f} Mbp genome (30% segmental duplications), 2x101 bp, -m -max_dup 10000 -all_sj" if WORKLOAD == "c5" else
+          f"BASELINE config[3] scaled x{SCALE}: {int(3.1e9 * SCALE / 1e6)} Mbp genome, pairs 2x250 bp, 3% substitutions + indels" if WORKLOAD == "c4" else
           f"BASELINE config[2] scaled x{SCALE}: {int(3.1e9 * SCALE / 1e6)} Mbp genome in 24 contigs with gene models, spliced pairs 2x101 bp, 1% substitutions")
-    return {"workload": wl, "pairs_per_gpu": sample_pairs or PAIRS_PER_GPU, "read_len": READ_LEN,
+    return {"workload": wl, "pairs_per_gpu": sample_pairs or PAIRS_PER_GPU, "read_len": 250 if WORKLOAD == "c4" else READ_LEN,
             "flags": ("-mis " + MIS) if MIS else "as named (no -mis: MaxMismatch=0, SURVEY.md F3)",
             "sharding": "contiguous read range per GPU, index replicated per HBM, no collective",
             "l2": "read batch (226 MB of codes per GPU) is larger than L2; " + ("the 4.6 MB Occ table of this config is L2-resident by nature"
@@ -204,6 +212,8 @@ def main():
     params = dict(pair_end=1)
     if MIS:
         params["max_mismatch"] = int(MIS)
+    if WORKLOAD == "c5":
+        params.update(multi_hit=1, max_dup=10000, all_sj=1)
     # CONTEXTS contexts (one host thread each, the C-ABI's unit of concurrency) share this GPU and split the step's batch:
     # their H2D / kernels / D2H overlap on separate streams.  Host cores are divided among ranks and contexts.
     cores = os.cpu_count() or 1
@@ -301,8 +311,8 @@ def main():
         if world == 1:
             try:
                 cores = os.cpu_count() or 1
-                extra = ["-mis", MIS] if MIS else []
-                sp = min(REF_SAMPLE_PAIRS, 100_000)
+                extra = (["-mis", MIS] if MIS else []) + (["-m", "-max_dup", "10000", "-all_sj"] if WORKLOAD == "c5" else [])
+                sp = min(REF_SAMPLE_PAIRS, 100_000 if WORKLOAD != "c4" else 40_000)
                 r1, r2, e1, e2 = reference_setup(g, idx, sp)
                 load = min(time_reference(idx, e1, e2, 2, cores, extra) for _ in range(2))
                 t = max(time_reference(idx, r1, r2, 2 * sp, cores, extra) - load, 1e-6)
