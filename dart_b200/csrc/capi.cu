@@ -8,9 +8,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <new>
 
 #include "context.h"
+#include "rank.cuh"
 
 using namespace dartgpu;
 
@@ -95,6 +99,7 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
     c->d_dev_off.reserve(n + 2); c->d_rlen.reserve(n + 1);
     const int64_t code_bytes = n_bases + 15ll * n + 16;      // upper bound of the padded layout
     c->d_codes.reserve(code_bytes);
+    c->d_packed.reserve(code_bytes / 16 + 1);
     c->n_code_bytes = code_bytes;
     cudaStream_t st = c->stream;
     DG_CUDA(cudaEventRecord(c->ev[0], st));
@@ -115,7 +120,7 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
         size_t tmp = scan_tmp_bytes(n);
         c->d_scan_tmp.reserve(tmp + 256);
         launch_scan_u32_to_i64(c->d_padded.p, c->d_dev_off.p, n, c->d_scan_tmp.p, tmp, st);
-        launch_encode_reads(c->d_raw.p, c->d_off.p, c->d_dev_off.p, n, c->d_codes.p, st);
+        launch_encode_reads(c->d_raw.p, c->d_off.p, c->d_dev_off.p, n, c->d_codes.p, c->d_packed.p, st);
         DG_CUDA(cudaGetLastError());
         c->stats.kernel_launches += 4;
     }
@@ -145,7 +150,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     a.cap_rec = c->cap_rec; a.max_dup = c->prm.max_dup; a.max_gaps = c->prm.max_gaps; a.max_intron = c->prm.max_intron;
     a.recs = c->d_recs.p; a.nrec = c->d_nrec.p; a.nhits = c->d_nhits.p; a.seed_off = c->d_seed_off.p;
     a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = c->d_big_count.p; a.mid_list = c->d_mid_list.p; a.mid_count = c->d_mid_count.p;
-    a.stats = c->d_stats.p;
+    a.stats = c->d_stats.p; a.packed = c->d_packed.p; a.steal = c->d_steal.p;
 
     DG_CUDA(cudaMemsetAsync(c->d_nhits.p + n, 0, sizeof(uint32_t), st));
     DG_CUDA(cudaEventRecord(c->ev[2], st));
@@ -322,6 +327,125 @@ static const uint8_t *upload_job_bases(dartgpu_ctx *c, const char *bases, int64_
 // ---------------------------------------------------------------------------------------------------
 // index hand-over
 // ---------------------------------------------------------------------------------------------------
+SharedIndex::~SharedIndex() { cudaSetDevice(device); }   // the DevBuf members free on the right device
+
+// identity of an index for sharing: header fields + a hash of samples of the tables
+static std::string index_key(int device, const dartgpu_index_view *v, int sa_shift, bool force64)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t x) { h = (h ^ x) * 1099511628211ull; };
+    mix(v->primary); mix(v->seq_len); mix(v->bwt_size); mix(v->sa_intv); mix(v->n_sa); mix((uint64_t)v->l_pac); mix((uint64_t)v->n_seqs);
+    for (int i = 0; i < 5; i++) mix(v->L2[i]);
+    const uint64_t step_b = std::max<uint64_t>(1, v->bwt_size / 4096), step_s = std::max<uint64_t>(1, v->n_sa / 4096);
+    for (uint64_t i = 0; i < v->bwt_size; i += step_b) mix(v->bwt[i]);
+    for (uint64_t i = 0; i < v->n_sa; i += step_s) mix(v->sa[i]);
+    for (int i = 0; i < v->n_seqs; i++) mix((uint64_t)v->seq_len_arr[i]);
+    char buf[96];
+    snprintf(buf, sizeof buf, "%d:%016llx:%d:%d", device, (unsigned long long)h, sa_shift, (int)force64);
+    return buf;
+}
+
+static std::mutex g_index_mutex;
+static std::map<std::string, std::weak_ptr<SharedIndex>> g_indexes;
+
+static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_index_view *v, cudaStream_t st)
+{
+    const bool force64 = getenv("DARTGPU_FORCE_IDX64") != nullptr;
+    const bool wide = force64 || v->seq_len + 2 >= (1ull << 32);
+    // how dense a suffix array to keep: DARTGPU_SA_SAMPLE=<power of two <= the file's interval> pins it (tests compare the
+    // LF-step counter with the reference's at 32); otherwise the densest one that fits a third of the free HBM
+    int file_shift = 0;
+    while ((1ull << file_shift) < v->sa_intv) file_shift++;
+    int sa_shift = -1;
+    if (const char *e = getenv("DARTGPU_SA_SAMPLE")) {
+        long want = atol(e);
+        if (want < 1 || (want & (want - 1)) || (uint64_t)want > v->sa_intv)
+            throw std::make_pair(DARTGPU_ERR_ARG, std::string("DARTGPU_SA_SAMPLE must be a power of two <= the index's SA interval"));
+        sa_shift = 0;
+        while ((1l << sa_shift) < want) sa_shift++;
+    }
+    const uint64_t n_blocks32 = (v->seq_len + 63) / 64;
+    const size_t occ_bytes = (n_blocks32 + 2) * 32, ref_words = (size_t)((2 * v->l_pac + 15) / 16 + 2);
+    const size_t sa_width = wide ? 8 : 4;
+    if (sa_shift < 0) {
+        size_t free_b = 0, total_b = 0;
+        DG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t fixed = occ_bytes + ref_words * 4 + v->n_sa * 8 + (64u << 20);
+        const size_t budget = free_b > fixed ? (free_b - fixed) / 3 : 0;
+        sa_shift = 0;
+        while (sa_shift < file_shift && ((v->seq_len >> sa_shift) + 2) * sa_width > budget) sa_shift++;
+    }
+
+    std::lock_guard<std::mutex> lock(g_index_mutex);
+    const std::string key = index_key(device, v, sa_shift, force64);
+    auto it = g_indexes.find(key);
+    if (it != g_indexes.end())
+        if (auto sp = it->second.lock()) return sp;
+
+    auto S = std::make_shared<SharedIndex>();
+    S->device = device; S->key = key; S->G = v->l_pac;
+    int64_t acc = 0;
+    std::vector<std::pair<int64_t, int>> ends;
+    for (int i = 0; i < v->n_seqs; i++) {
+        S->names.push_back(v->seq_names && v->seq_names[i] ? v->seq_names[i] : ("seq" + std::to_string(i)));
+        S->chr_len.push_back(v->seq_len_arr[i]);
+        S->chr_fwd.push_back(acc);
+        acc += v->seq_len_arr[i];
+        ends.push_back({S->chr_fwd[i] + v->seq_len_arr[i] - 1, i});          // forward copy
+        ends.push_back({2 * S->G - acc + v->seq_len_arr[i] - 1, i});         // reverse-complement copy
+    }
+    std::sort(ends.begin(), ends.end());
+    for (auto &p : ends) { S->ends.push_back(p.first); S->end_chr.push_back(p.second); }
+
+    DevIndex &ix = S->ix;
+    ix.n_blocks32 = n_blocks32;
+    ix.sa_shift = sa_shift; ix.sa_mask = (1ull << sa_shift) - 1; ix.sa_wide = wide;
+    ix.primary = v->primary; ix.seq_len = v->seq_len;
+    for (int i = 0; i < 5; i++) ix.L2[i] = v->L2[i];
+    ix.G = S->G; ix.n_ends = (int)S->ends.size(); ix.force64 = force64;
+
+    // Occ blocks: raw BWA words up, re-laid-out on the device
+    const uint64_t n_blocks128 = (v->seq_len + 127) / 128;
+    if (v->bwt_size < n_blocks128 * 16 - 8) throw std::make_pair(DARTGPU_ERR_INDEX, std::string(".bwt is shorter than its header implies"));
+    {
+        DevBuf<uint32_t> raw;
+        const uint64_t n_words = std::min<uint64_t>(v->bwt_size, n_blocks128 * 16);
+        raw.reserve(n_words + 16);
+        DG_CUDA(cudaMemcpyAsync(raw.p, v->bwt, n_words * 4, cudaMemcpyHostToDevice, st));
+        S->d_occ32.reserve(occ_bytes);
+        launch_relayout_occ32(raw.p, n_words, reinterpret_cast<Occ32 *>(S->d_occ32.p), n_blocks32, st);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaStreamSynchronize(st));
+    }
+    ix.occ32 = reinterpret_cast<const Occ32 *>(S->d_occ32.p);
+    {
+        DevBuf<uint64_t> sa_file;
+        sa_file.reserve(v->n_sa);
+        DG_CUDA(cudaMemcpyAsync(sa_file.p, v->sa, v->n_sa * 8, cudaMemcpyHostToDevice, st));
+        S->d_sa.reserve(((v->seq_len >> sa_shift) + 2) * sa_width);
+        ix.sa = S->d_sa.p;
+        launch_sa_densify(ix, sa_file.p, v->sa_intv, v->n_sa, S->d_sa.p, st);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaStreamSynchronize(st));
+    }
+    {
+        DevBuf<uint8_t> dpac;
+        const size_t pac_bytes = (size_t)v->l_pac / 4 + 1;
+        dpac.reserve(pac_bytes);
+        DG_CUDA(cudaMemcpyAsync(dpac.p, v->pac, pac_bytes, cudaMemcpyHostToDevice, st));
+        S->d_ref2.reserve(ref_words);
+        launch_build_ref2(dpac.p, S->d_ref2.p, S->G, st);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaStreamSynchronize(st));
+    }
+    S->d_ends.reserve(S->ends.size());
+    DG_CUDA(cudaMemcpyAsync(S->d_ends.p, S->ends.data(), S->ends.size() * 8, cudaMemcpyHostToDevice, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    ix.ref2 = S->d_ref2.p; ix.chr_ends = S->d_ends.p;
+    g_indexes[key] = S;
+    return S;
+}
+
 static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
 {
     if (!v || !v->bwt || !v->sa || !v->pac || v->n_seqs <= 0 || !v->seq_len_arr)
@@ -341,60 +465,11 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
     DG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto &ev : c->ev) DG_CUDA(cudaEventCreate(&ev));
-    cudaStream_t st = c->stream;
-
-    c->G = v->l_pac;
-    int64_t acc = 0;
-    std::vector<std::pair<int64_t, int>> ends;
-    for (int i = 0; i < v->n_seqs; i++) {
-        c->names.push_back(v->seq_names && v->seq_names[i] ? v->seq_names[i] : ("seq" + std::to_string(i)));
-        c->chr_len.push_back(v->seq_len_arr[i]);
-        c->chr_fwd.push_back(acc);
-        acc += v->seq_len_arr[i];
-        ends.push_back({c->chr_fwd[i] + v->seq_len_arr[i] - 1, i});          // forward copy
-        ends.push_back({2 * c->G - acc + v->seq_len_arr[i] - 1, i});         // reverse-complement copy
-    }
-    std::sort(ends.begin(), ends.end());
-    for (auto &p : ends) { c->ends.push_back(p.first); c->end_chr.push_back(p.second); }
-    c->pac.assign(v->pac, v->pac + v->l_pac / 4 + 1);
-
-    // Occ blocks: raw words up, re-laid-out on the device
-    const uint64_t n_blocks = (v->seq_len + 127) / 128;
-    if (v->bwt_size < n_blocks * 16 - 8) throw std::make_pair(DARTGPU_ERR_INDEX, std::string(".bwt is shorter than its header implies"));
-    {
-        DevBuf<uint32_t> raw;
-        raw.reserve(n_blocks * 16 + 16);
-        DG_CUDA(cudaMemsetAsync(raw.p, 0, (n_blocks * 16 + 16) * 4, st));
-        DG_CUDA(cudaMemcpyAsync(raw.p, v->bwt, std::min<uint64_t>(v->bwt_size, n_blocks * 16 + 16) * 4, cudaMemcpyHostToDevice, st));
-        c->d_occ.reserve(n_blocks * 4);
-        launch_relayout_occ(raw.p, c->d_occ.p, n_blocks, st);
-        DG_CUDA(cudaGetLastError());
-        DG_CUDA(cudaStreamSynchronize(st));
-    }
-    c->d_sa.reserve(v->n_sa);
-    DG_CUDA(cudaMemcpyAsync(c->d_sa.p, v->sa, v->n_sa * 8, cudaMemcpyHostToDevice, st));
-    {
-        DevBuf<uint8_t> dpac;
-        dpac.reserve(c->pac.size());
-        DG_CUDA(cudaMemcpyAsync(dpac.p, c->pac.data(), c->pac.size(), cudaMemcpyHostToDevice, st));
-        c->d_ref2.reserve((2 * c->G + 15) / 16 + 2);
-        launch_build_ref2(dpac.p, c->d_ref2.p, c->G, st);
-        DG_CUDA(cudaGetLastError());
-        DG_CUDA(cudaStreamSynchronize(st));
-    }
-    c->d_ends.reserve(c->ends.size());
-    DG_CUDA(cudaMemcpyAsync(c->d_ends.p, c->ends.data(), c->ends.size() * 8, cudaMemcpyHostToDevice, st));
-    c->d_stats.reserve(1); c->h_total.reserve(2); c->h_dstats.reserve(1);
-    DG_CUDA(cudaStreamSynchronize(st));
-
-    DevIndex &ix = c->ix;
-    ix.occ = c->d_occ.p; ix.n_blocks = n_blocks; ix.sa = c->d_sa.p;
-    ix.sa_mask = v->sa_intv - 1; ix.sa_shift = 0;
-    while ((1ull << ix.sa_shift) < v->sa_intv) ix.sa_shift++;
-    ix.primary = v->primary; ix.seq_len = v->seq_len;
-    for (int i = 0; i < 5; i++) ix.L2[i] = v->L2[i];
-    ix.ref2 = c->d_ref2.p; ix.G = c->G; ix.chr_ends = c->d_ends.p; ix.n_ends = (int)c->ends.size();
-    ix.force64 = getenv("DARTGPU_FORCE_IDX64") != nullptr;
+    c->shared = load_shared_index(c->device, v, c->stream);
+    c->ix = c->shared->ix;
+    c->G = c->shared->G;
+    c->d_stats.reserve(1); c->h_total.reserve(2); c->h_dstats.reserve(1); c->d_steal.reserve(4);
+    DG_CUDA(cudaStreamSynchronize(c->stream));
 }
 
 static bool slurp(const std::string &fn, std::vector<uint8_t> &buf)
@@ -508,9 +583,9 @@ int dartgpu_set_params(dartgpu_ctx *c, const dartgpu_params *p)
 }
 const char *dartgpu_last_error(const dartgpu_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 int64_t dartgpu_genome_size(const dartgpu_ctx *c) { return c ? c->G : 0; }
-int dartgpu_num_sequences(const dartgpu_ctx *c) { return c ? (int)c->names.size() : 0; }
-const char *dartgpu_sequence_name(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->names.size()) ? c->names[i].c_str() : ""; }
-int64_t dartgpu_sequence_length(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->chr_len.size()) ? c->chr_len[i] : 0; }
+int dartgpu_num_sequences(const dartgpu_ctx *c) { return c ? (int)c->shared->names.size() : 0; }
+const char *dartgpu_sequence_name(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->shared->names.size()) ? c->shared->names[i].c_str() : ""; }
+int64_t dartgpu_sequence_length(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->shared->chr_len.size()) ? c->shared->chr_len[i] : 0; }
 int dartgpu_set_stream(dartgpu_ctx *c, void *s)
 {
     if (!c) return DARTGPU_ERR_ARG;

@@ -2,10 +2,32 @@
 // orchestration (pipeline.cu) shares with the stage entry points (capi.cu).
 #pragma once
 #include <chrono>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "dartgpu_internal.h"
+
+namespace dartgpu {
+// Everything that is read-only after load.  One copy per device: contexts created from the same index on the same device
+// (one per host thread, the C-ABI's unit of concurrency) share it, so 180 GB of HBM hold one human-sized index plus its
+// full suffix array instead of one per thread.
+struct SharedIndex {
+    int device = 0;
+    std::string key;
+    DevIndex ix{};
+    int64_t G = 0;
+    std::vector<std::string> names;
+    std::vector<int64_t> chr_len, chr_fwd;
+    std::vector<int64_t> ends;      // sorted ChrLocMap keys (/root/reference/src/bwt_index.cpp:249-250)
+    std::vector<int> end_chr;       // ChrLocMap values
+    DevBuf<uint8_t> d_occ32;        // Occ32 blocks
+    DevBuf<uint8_t> d_sa;           // u32 or u64 entries
+    DevBuf<uint32_t> d_ref2;
+    DevBuf<int64_t> d_ends;
+    ~SharedIndex();
+};
+} // namespace dartgpu
 
 struct dartgpu_ctx {
     int device = 0;
@@ -13,20 +35,10 @@ struct dartgpu_ctx {
     dartgpu_params prm{};
     std::string err;
 
-    // ---- host-side view of the index (orchestration needs reference bases and the sequence table) ----
-    int64_t G = 0;
-    std::vector<std::string> names;
-    std::vector<int64_t> chr_len, chr_fwd;
-    std::vector<int64_t> ends;      // sorted ChrLocMap keys (/root/reference/src/bwt_index.cpp:249-250)
-    std::vector<int> end_chr;       // ChrLocMap values
-    std::vector<uint8_t> pac;       // forward strand, 2 bits per base
-
-    // ---- device-resident index ----
+    // ---- the index: device tables + the sequence table, shared by every context on the same device ----
+    std::shared_ptr<dartgpu::SharedIndex> shared;
     dartgpu::DevIndex ix{};
-    dartgpu::DevBuf<ulonglong2> d_occ;
-    dartgpu::DevBuf<uint64_t> d_sa;
-    dartgpu::DevBuf<uint32_t> d_ref2;
-    dartgpu::DevBuf<int64_t> d_ends;
+    int64_t G = 0;
 
     // ---- read batch on the device ----
     int n_reads = 0, max_rlen = 0, cap_rec = 0;
@@ -37,6 +49,8 @@ struct dartgpu_ctx {
     dartgpu::DevBuf<int64_t> d_off;
     dartgpu::DevBuf<uint32_t> d_padded;
     dartgpu::DevBuf<uint8_t> d_codes;
+    dartgpu::DevBuf<uint2> d_packed;         // the search kernel's 2-bit view of the batch
+    dartgpu::DevBuf<uint32_t> d_steal;
     dartgpu::DevBuf<int64_t> d_dev_off;
     dartgpu::DevBuf<int32_t> d_rlen;
 
@@ -106,15 +120,6 @@ void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs
 // the whole per-read path over the uploaded batch
 void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out);                              // device orchestration
 void free_device_pipe(void *p);
-
-inline int host_ref_code(const dartgpu_ctx *c, int64_t p)
-{
-    if (p < 0 || p >= 2 * c->G) return 0;
-    if (p < c->G) return (c->pac[p >> 2] >> ((~p & 3) << 1)) & 3;
-    int64_t q = 2 * c->G - 1 - p;
-    return 3 - ((c->pac[q >> 2] >> ((~q & 3) << 1)) & 3);
-}
-inline char host_ref_char(const dartgpu_ctx *c, int64_t p) { return "ACGT"[host_ref_code(c, p)]; }
 
 struct Timer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();

@@ -13,18 +13,22 @@ namespace dartgpu {
 // ---------------------------------------------------------------------------------------------------
 // Device-resident index (replicated into every GPU's HBM once, at context creation)
 // ---------------------------------------------------------------------------------------------------
-// Occ table: one 64-byte block per 128 BWT symbols, re-laid-out from the BWA block (4 x u64 counts followed
-// by 8 x u32 of symbols, /root/reference/src/BWT_Index/bwtindex.c:53-75) into four 16-byte quarters
-//     quarter q = { u64 count of symbol q before the block, u64 symbols [32q, 32q+32) of the block }
-// so that the 4 lanes of a search group each issue ONE 128-bit load (together one 64-byte segment) and
-// each lane owns the count it needs plus a quarter of the popcount work.  Symbol j of a quarter sits at
-// bits 62-2j (first symbol in the top bits, as in the BWA words).
+// Occ table: BWA's 64-byte block per 128 BWT symbols (4 x u64 counts followed by 8 x u32 of symbols,
+// /root/reference/src/BWT_Index/bwtindex.c:53-75) is re-laid-out on the GPU into Occ32 blocks (rank.cuh): 32 bytes = one
+// sector per 64 symbols, {u32 count[4], u64 low bit-plane, u64 high bit-plane}, so that ONE thread resolves a rank query
+// with one 128-bit load + one 32-bit load from a single sector.
+// Suffix array: the file holds every 32nd entry (bwt_cal_sa, /root/reference/src/BWT_Index/bwt.c:101-123).  HBM has room
+// for more, so at load the GPU walks the LF mapping once over the whole text and materialises every 2^sa_shift-th entry
+// (shift 0 = the full suffix array when it fits the memory budget): locate becomes one gather instead of ~31 dependent
+// LF steps per hit.  Entries are u32 when the text length fits 32 bits, u64 otherwise.
+struct Occ32;
 struct DevIndex {
-    const ulonglong2 *occ;   // n_blocks * 4 quarters
-    uint64_t n_blocks;
-    const uint64_t *sa;      // sampled suffix array, sa[0] = (uint64_t)-1 (/root/reference/src/bwt_index.cpp:31)
-    uint64_t sa_mask;        // sa_intv - 1
-    int sa_shift;            // log2(sa_intv)
+    const Occ32 *occ32;      // n_blocks32 blocks (+1 zero guard block)
+    uint64_t n_blocks32;
+    const void *sa;          // sa[i >> sa_shift] = SA[i] for i % 2^sa_shift == 0; entry 0 is never read (it stands for -1)
+    uint64_t sa_mask;        // 2^sa_shift - 1
+    int sa_shift;
+    int sa_wide;             // 1: u64 entries, 0: u32
     uint64_t primary, seq_len;
     uint64_t L2[5];
     const uint32_t *ref2;    // reference over [0,2G), 2 bits/base, 16 bases per word, base i at bits 30-2(i&15)
@@ -92,14 +96,18 @@ template <class T> struct PinBuf {
 // kernel launchers (each file owns its kernels; all work is enqueued on `st`)
 // ---------------------------------------------------------------------------------------------------
 // index_device.cu
-void launch_relayout_occ(const uint32_t *bwt_words, ulonglong2 *occ, uint64_t n_blocks, cudaStream_t st);
+void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *occ, uint64_t n_blocks32, cudaStream_t st);
+// sa_file: the reference's sampled SA (every sa_intv-th entry, entry 0 = -1) on the device; out: every 2^shift-th entry
+void launch_sa_densify(const DevIndex &ix, const uint64_t *sa_file, uint64_t sa_intv, uint64_t n_sa_file, void *out, cudaStream_t st);
 void launch_build_ref2(const uint8_t *pac, uint32_t *ref2, int64_t G, cudaStream_t st);
 void launch_read_layout(const int64_t *off, int n, int32_t *rlen, uint32_t *padded, cudaStream_t st);
-void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, cudaStream_t st);
+void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, uint2 *packed, cudaStream_t st);
 
 // seed_kernels.cu
 struct SeedLaunch {
     const uint8_t *codes; const int64_t *dev_off; const int32_t *rlen; int n_reads;
+    const uint2 *packed;                                        // 16 bases per entry: .x = 2-bit codes (base i at bits 2i), .y = "not ACGT" bits
+    uint32_t *steal; int steal_base;                            // work-stealing counter for the tail of the search kernel
     int cap_rec; uint32_t max_dup; int max_gaps, max_intron;
     SearchRec *recs; uint32_t *nrec; uint32_t *nhits;          // search output
     int64_t *seed_off;                                          // n_reads+1, exclusive scan of nhits
@@ -110,7 +118,7 @@ struct SeedLaunch {
     uint64_t *big_scratch; size_t big_scratch_per_cta;          // global sort scratch for reads that exceed smem
     DevStats *stats;
 };
-void launch_search(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st);
+void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st);
 void launch_scan_hits(const SeedLaunch &a, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t scan_tmp_bytes(int n);
 void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, int64_t total_seeds, cudaStream_t st);

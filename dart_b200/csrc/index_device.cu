@@ -2,31 +2,90 @@
 // File formats: /root/reference/src/bwt_index.cpp:15-35 (.sa), :102-121 (.bwt), :193-212 (.pac decode);
 // block interleave written by /root/reference/src/BWT_Index/bwtindex.c:53-75.
 #include "dartgpu_internal.h"
+#include "rank.cuh"
 
 namespace dartgpu {
 
-// BWA block = 8 words of counts (4 x u64, little endian) + up to 8 words of symbols (16 per word, first
-// symbol in the top bits).  Output quarter q = { count[q], symbols[32q..32q+32) as one u64 }.
-__global__ void k_relayout_occ(const uint32_t *__restrict__ w, ulonglong2 *__restrict__ occ, uint64_t n_quarters)
+// BWA block (128 symbols) = 8 words of counts (4 x u64, little endian) + 8 words of symbols (16 per word, first symbol
+// in the top bits).  Output: two Occ32 blocks (rank.cuh) per BWA block; the second one's counts include the first half.
+__global__ void k_relayout_occ32(const uint32_t *__restrict__ w, uint64_t n_words, Occ32 *__restrict__ occ, uint64_t n_blocks32)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; t < n_quarters; t += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t b = t >> 2;
-        int q = (int)(t & 3);
-        const uint32_t *p = w + b * 16;
-        ulonglong2 o;
-        o.x = (uint64_t)p[2 * q] | (uint64_t)p[2 * q + 1] << 32;
-        o.y = (uint64_t)p[8 + 2 * q] << 32 | (uint64_t)p[8 + 2 * q + 1];
+    for (; t <= n_blocks32; t += (uint64_t)gridDim.x * blockDim.x) {   // one guard block past the end
+        const uint64_t B = t >> 1;
+        const int h = (int)(t & 1);
+        auto word = [&](uint64_t i) -> uint32_t { return i < n_words ? w[i] : 0u; };
+        const uint64_t base = B * 16;
+        uint64_t cnt[4];
+        for (int c = 0; c < 4; c++) cnt[c] = (uint64_t)word(base + 2 * c) | (uint64_t)word(base + 2 * c + 1) << 32;
+        uint64_t lo[2] = {0, 0}, hi[2] = {0, 0};
+        for (int half = 0; half <= h; half++)
+            for (int j = 0; j < 4; j++) {
+                const uint32_t x = word(base + 8 + 4 * half + j);
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t sym = (x >> (30 - 2 * i)) & 3u;
+                    lo[half] |= (uint64_t)(sym & 1u) << (16 * j + i);
+                    hi[half] |= (uint64_t)(sym >> 1) << (16 * j + i);
+                }
+            }
+        if (h) {
+            cnt[0] += __popcll(~hi[0] & ~lo[0]); cnt[1] += __popcll(~hi[0] & lo[0]);
+            cnt[2] += __popcll(hi[0] & ~lo[0]);  cnt[3] += __popcll(hi[0] & lo[0]);
+        }
+        Occ32 o;
+        for (int c = 0; c < 4; c++) o.cnt[c] = (uint32_t)cnt[c];
+        o.lo = lo[h]; o.hi = hi[h];
         occ[t] = o;
     }
 }
 
-void launch_relayout_occ(const uint32_t *bwt_words, ulonglong2 *occ, uint64_t n_blocks, cudaStream_t st)
+void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *occ, uint64_t n_blocks32, cudaStream_t st)
 {
-    uint64_t nq = n_blocks * 4;
-    int grid = (int)((nq + 255) / 256 < 148 * 16 ? (nq + 255) / 256 : 148 * 16);
+    uint64_t want = (n_blocks32 + 1 + 255) / 256;
+    int grid = (int)(want < 148 * 16 ? want : 148 * 16);
     if (grid < 1) grid = 1;
-    k_relayout_occ<<<grid, 256, 0, st>>>(bwt_words, occ, nq);
+    k_relayout_occ32<<<grid, 256, 0, st>>>(bwt_words, n_words, occ, n_blocks32);
+}
+
+// One pass of the LF mapping over the whole text: every entry of the file's sampled SA starts a walker that writes
+// SA[k] = v, steps k -> LF(k), v -> v-1, and stops at the next sampled index (which another walker owns).  Together the
+// walkers visit every SA index exactly once; entries at multiples of 2^shift are kept.  bwt_invPsi:
+// /root/reference/src/bwt_search.cpp:119-125.
+template <typename SaT>
+__global__ void k_sa_densify(DevIndex ix, const uint64_t *__restrict__ sa_file, uint64_t sa_intv, uint64_t n_sa_file, SaT *__restrict__ out)
+{
+    __shared__ uint64_t s_L2[4];
+    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; }
+    __syncthreads();
+    const char *occ = reinterpret_cast<const char *>(ix.occ32);
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; j < n_sa_file; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t k = j * sa_intv;
+        uint64_t v = j == 0 ? ix.seq_len : sa_file[j];     // SA[0] is the empty suffix at position seq_len (kept as -1 in the file)
+        for (;;) {
+            if ((k & ix.sa_mask) == 0) out[k >> ix.sa_shift] = (SaT)v;
+            if (k == ix.primary) k = 0;
+            else {
+                const uint64_t kk = k - (k > ix.primary);
+                const char *blk = occ + (kk >> 6) * 32;
+                const ulonglong2 pl = __ldg(reinterpret_cast<const ulonglong2 *>(blk + 16));
+                const uint32_t t = (uint32_t)kk & 63u;
+                const int c = occ32_symbol(pl.x, pl.y, t);
+                k = s_L2[c] + __ldg(reinterpret_cast<const uint32_t *>(blk) + c) + occ32_eq_upto(pl.x, pl.y, c, t);
+            }
+            v--;
+            if ((k & (sa_intv - 1)) == 0) break;
+        }
+    }
+}
+
+void launch_sa_densify(const DevIndex &ix, const uint64_t *sa_file, uint64_t sa_intv, uint64_t n_sa_file, void *out, cudaStream_t st)
+{
+    uint64_t want = (n_sa_file + 255) / 256;
+    int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+    if (grid < 1) grid = 1;
+    if (ix.sa_wide) k_sa_densify<uint64_t><<<grid, 256, 0, st>>>(ix, sa_file, sa_intv, n_sa_file, (uint64_t *)out);
+    else k_sa_densify<uint32_t><<<grid, 256, 0, st>>>(ix, sa_file, sa_intv, n_sa_file, (uint32_t *)out);
 }
 
 // RefSequence over both strands, 2 bits per base: position p < G is the .pac base, position p >= G is the
@@ -78,7 +137,7 @@ __global__ void k_read_layout(const int64_t *__restrict__ off, int n, int32_t *r
 
 // codes: 0..3 = ACGT, 8..11 = acgt, 5 = 'N', 4 = anything else (dartgpu_internal.h)
 __global__ void k_encode_reads(const uint8_t *__restrict__ raw, const int64_t *__restrict__ off, const int64_t *__restrict__ dev_off,
-                               int n, uint8_t *codes)
+                               int n, uint8_t *codes, uint2 *packed)
 {
     __shared__ uint8_t tab[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -101,13 +160,17 @@ __global__ void k_encode_reads(const uint8_t *__restrict__ raw, const int64_t *_
         uint4 *dst = reinterpret_cast<uint4 *>(codes + dev_off[r]);
         for (int ch = lane; ch < chunks; ch += 32) {
             uint32_t w[4] = {0, 0, 0, 0};
+            uint32_t two = 0, amb = 0;      // the search kernel's view: 2 bits per base + one "not ACGT" bit
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 int p = ch * 16 + k;
                 uint32_t c = p < rl ? tab[raw[src + p]] : 4u;
                 w[k >> 2] |= c << (8 * (k & 3));
+                two |= (c & 3u) << (2 * k);
+                amb |= ((c >> 2) & 1u) << k;
             }
             dst[ch] = make_uint4(w[0], w[1], w[2], w[3]);
+            packed[(dev_off[r] >> 4) + ch] = make_uint2(two, amb);
         }
     }
 }
@@ -117,11 +180,11 @@ void launch_read_layout(const int64_t *off, int n, int32_t *rlen, uint32_t *padd
     int grid = (n + 1 + 255) / 256; if (grid > 148 * 8) grid = 148 * 8;
     k_read_layout<<<grid, 256, 0, st>>>(off, n, rlen, padded);
 }
-void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, cudaStream_t st)
+void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, uint2 *packed, cudaStream_t st)
 {
     int64_t want = ((int64_t)n * 32 + 255) / 256;
     int grid = (int)(want < 148 * 16 ? want : 148 * 16); if (grid < 1) grid = 1;
-    k_encode_reads<<<grid, 256, 0, st>>>(raw, off, dev_off, n, codes);
+    k_encode_reads<<<grid, 256, 0, st>>>(raw, off, dev_off, n, codes, packed);
 }
 
 } // namespace dartgpu

@@ -311,9 +311,9 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     D->h_vals.reserve(8); D->h_counters.reserve(8); D->counters.reserve(8); D->work.reserve(4); D->h_work.reserve(4);
     DG_CUDA(cudaMemsetAsync(D->work.p, 0, 4 * sizeof(unsigned long long), st));
     if (!D->tables) {
-        D->d_chr_fwd.reserve(c->chr_fwd.size()); D->d_end_chr.reserve(c->end_chr.size());
-        DG_CUDA(cudaMemcpyAsync(D->d_chr_fwd.p, c->chr_fwd.data(), c->chr_fwd.size() * 8, cudaMemcpyHostToDevice, st));
-        std::vector<int32_t> ec(c->end_chr.begin(), c->end_chr.end());
+        D->d_chr_fwd.reserve(c->shared->chr_fwd.size()); D->d_end_chr.reserve(c->shared->end_chr.size());
+        DG_CUDA(cudaMemcpyAsync(D->d_chr_fwd.p, c->shared->chr_fwd.data(), c->shared->chr_fwd.size() * 8, cudaMemcpyHostToDevice, st));
+        std::vector<int32_t> ec(c->shared->end_chr.begin(), c->shared->end_chr.end());
         DG_CUDA(cudaMemcpyAsync(D->d_end_chr.p, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice, st));
         DG_CUDA(cudaStreamSynchronize(st));
         D->tables = true;
@@ -344,7 +344,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     Env E{};
     E.P = PhaseParams{P.max_gaps, P.max_intron, P.min_intron, P.max_mismatch, P.multi_hit, P.pair_end, P.all_sj};
     E.ref = RefView{c->ix.ref2, nullptr, c->G}; E.G = c->G;
-    E.ends = c->d_ends.p; E.end_chr = D->d_end_chr.p; E.n_ends = (int)c->ends.size(); E.chr_fwd = D->d_chr_fwd.p;
+    E.ends = c->shared->d_ends.p; E.end_chr = D->d_end_chr.p; E.n_ends = (int)c->shared->ends.size(); E.chr_fwd = D->d_chr_fwd.p;
     E.codes = c->d_codes.p; E.code_off = c->d_dev_off.p; E.rlen = c->d_rlen.p; E.keys = c->d_keys.p;
     E.cs = D->cs.p; E.pool = D->pool.p;
     E.kjobs = D->kjobs.p; E.kjob_count = D->counters.p + 0; E.khits = D->khits.p;

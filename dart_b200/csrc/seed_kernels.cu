@@ -6,16 +6,21 @@
 // (IdentifySeedPairs, GenerateAlignmentCandidate).
 //
 // Execution model
-//   * a GROUP of 4 lanes owns one read at a time; 8 groups per warp run 8 independent FM chains.
-//     One rank query = one 128-bit load per lane = one 64-byte Occ block per group, each lane
-//     popcounting its own 32 symbols (2 POPC: "equal to c" and "greater than c"), combined with xor-shuffles.
-//   * the nested loops of the reference (reads > search starts > extension steps) are flattened into a
-//     single loop whose every iteration performs exactly one rank step, so the 8 groups of a warp stay
-//     converged although their reads, search starts and match lengths differ.
-//   * reads are staged in shared memory 2-bit packed (+ a 1-bit "not ACGT" plane).
+//   * ONE THREAD owns one FM chain.  A rank query is one 128-bit load (the two bit-planes of 64 symbols) plus one 32-bit
+//     load (the count of the wanted symbol) from a single 32-byte sector (Occ32, rank.cuh), one masked popcount and no
+//     cross-lane traffic.  Round-1 history: the first kernels ranked a 64-byte block with 4 cooperating lanes
+//     (4 x 128-bit loads, popcounts combined with shuffles); ncu showed them bound by the integer pipes (~100
+//     instructions per LANE per step, i.e. ~400 thread-instructions per step) with the 4.6 MB table L2-resident, and by
+//     too few independent chains in flight once the table lives in HBM.  Thread-per-chain needs ~6x fewer
+//     thread-instructions per step, puts 4x more chains in flight per SM and touches half the bytes per query.
+//   * the nested loops of the reference (reads > search starts > extension steps) are flattened into a single loop whose
+//     every iteration performs exactly one rank step, so the 32 lanes of a warp stay converged although their reads,
+//     search starts and match lengths differ; a lane draws its next read the moment it finishes one.
+//   * reads arrive 2-bit packed (+1 bit "not ACGT"), 16 bases per 8-byte entry, written by k_encode_reads.
 //   * search only records SA intervals (of the reverse-complemented pattern, see k_search); after a prefix sum over
-//     the hit counts a second kernel resolves every hit with its own group (LF walk to the next SA sample, then the
-//     mirror p -> 2G - p - len), so repetitive reads do not serialise.
+//     the hit counts a second kernel resolves every hit with its own thread (LF walk to the next kept SA entry — none at
+//     all when the full suffix array is resident — then the mirror p -> 2G - p - len), so repetitive reads do not
+//     serialise.
 //   * seeds are 64-bit keys (gPos | rPos | len): sorting the keys is the reference's CompByGenomePos order.
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -28,35 +33,22 @@
 namespace dartgpu {
 
 constexpr int SEARCH_THREADS = 128;
-constexpr int GROUPS_PER_CTA = SEARCH_THREADS / 4;
-constexpr int RWORDS = DARTGPU_MAX_RLEN / 16;
 constexpr unsigned FULL = 0xffffffffu;
 
-// ---------------------------------------------------------------------------------------------------
-// rank primitives (rank.cuh holds the per-quarter arithmetic, unit-tested on the host)
-// ---------------------------------------------------------------------------------------------------
-// stage one read in the group's shared-memory slot: 2 bits per base + 1 ambiguity bit per base
-__device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, int rl, uint32_t *pk, uint16_t *am,
-                                           int q, unsigned gmask)
+// Occ(c, kk): occurrences of c in B[0..kk] (kk already adjusted for the primary row), bwt_occ (bwt_search.cpp:43-65)
+__device__ __forceinline__ uint32_t occ_rank(const char *occ, uint64_t kk, int c)
 {
-    int nw = (rl + 15) >> 4;
-    __syncwarp(gmask);
-    for (int w = q; w < nw; w += 4) {
-        uint4 v = *reinterpret_cast<const uint4 *>(codes + off + 16 * (int64_t)w);
-        uint32_t x[4] = {v.x, v.y, v.z, v.w};
-        uint32_t p2 = 0, a = 0;
+    const char *blk = occ + (kk >> 6) * 32;
+    const ulonglong2 pl = __ldg(reinterpret_cast<const ulonglong2 *>(blk + 16));
+    const uint32_t cnt = __ldg(reinterpret_cast<const uint32_t *>(blk) + c);
+    return cnt + occ32_eq_upto(pl.x, pl.y, c, (uint32_t)kk & 63u);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t t = x[i];
-            uint32_t two = (t & 3u) | ((t >> 6) & 0xCu) | ((t >> 12) & 0x30u) | ((t >> 18) & 0xC0u);
-            uint32_t ab = ((t >> 2) & 1u) | ((t >> 9) & 2u) | ((t >> 16) & 4u) | ((t >> 23) & 8u);
-            p2 |= two << (8 * i);
-            a |= ab << (4 * i);
-        }
-        pk[w] = p2;
-        am[w] = (uint16_t)a;
-    }
-    __syncwarp(gmask);
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -70,50 +62,31 @@ __device__ __forceinline__ void stage_read(const uint8_t *codes, int64_t off, in
 // forward by base b is then a plain backward step of revcomp(P) with c = 3 - b:
 //     n2   = Occ(c,l) - Occ(c,k)          size of the new interval          (k = x1-1, l = x1-1+x2)
 //     x1'  = L2[c] + 1 + Occ(c,k)         its start
-// i.e. one "equal to c" popcount per block and no forward-interval bookkeeping at all (round-1 ncu: the kernel is bound
-// by the integer pipes, not by memory; dropping x0 removes ~30 % of the step's instructions).
-// Occ(c,.) = block header count (lane c holds it) + in-block count; the in-block parts of the 4 lanes are summed as two
-// 8-bit fields of one word (two xor-shuffles), the header difference travels as a 32-bit value (interval widths are
-// < 2^32, checked at index load).  IdxT = uint32_t when the whole text fits 32 bits (every tested genome and BASELINE
-// configs 1, 2, 5), uint64_t otherwise (3.1 Gbp: 2G = 6.2e9) — same code, narrower interval arithmetic.
+// i.e. one "equal to c" popcount per query and no forward-interval bookkeeping at all.  Interval widths are < 2^32
+// (checked at index load); IdxT = uint32_t when the whole text fits 32 bits (every tested genome and BASELINE configs
+// 1, 2, 5), uint64_t otherwise (3.1 Gbp: 2G = 6.2e9) — same code, narrower interval arithmetic.
+//
+// Reads are handed out dynamically: a CTA first drains its own contiguous range through a shared-memory counter, then
+// steals single reads from a global counter that covers the last part of the batch, so that no lane idles while another
+// still has a queue (the grid is exactly one wave).  Results are indexed by read, so the order does not matter.
+// The work counters keep the reference's definition (a step touches one 64-byte BWA block or two, bwt_search.cpp:88-93).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_tables(const DevIndex &ix, uint64_t *s_L2, uint32_t *s_mask)
-{
-    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
-    if (threadIdx.x < 33) s_mask[threadIdx.x] = prefix_mask32((int)threadIdx.x);
-    __syncthreads();
-}
-
 template <typename IdxT>
-__global__ void __launch_bounds__(SEARCH_THREADS, 16)
-k_search(DevIndex ix, SeedLaunch a)
+__global__ void __launch_bounds__(SEARCH_THREADS)
+k_search(DevIndex ix, SeedLaunch a, int per_cta)
 {
-    __shared__ uint32_t s_pk[GROUPS_PER_CTA][RWORDS];
-    __shared__ uint16_t s_am[GROUPS_PER_CTA][RWORDS];
     __shared__ uint64_t s_L2[5];
-    __shared__ uint32_t s_mask[33];
-
-    const int lane = threadIdx.x & 31, q = lane & 3;
-    const unsigned gmask = 0xFu << (lane & ~3);
-    const int grp = threadIdx.x >> 2;
-    stage_tables(ix, s_L2, s_mask);
-    uint32_t *pk = s_pk[grp];
-    uint16_t *am = s_am[grp];
-    const IdxT primary = (IdxT)ix.primary;
-    const char *occq = reinterpret_cast<const char *>(ix.occ + q);   // this lane's quarter of block 0
-    const int q32 = 32 * q - 1;
-    // Reads are handed out dynamically: the CTA owns a contiguous range and its 32 groups draw the next read from a
-    // shared counter when they finish one (round-1 ncu: with a static stride a quarter of the lanes idled in the step
-    // waiting for the warp's slowest group).  Results are indexed by read, so the order does not matter.
     __shared__ int s_next;
-    const int per_cta = (a.n_reads + gridDim.x - 1) / gridDim.x;
-    const int r_end = min(a.n_reads, (int)(blockIdx.x + 1) * per_cta);
+    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
     if (threadIdx.x == 0) s_next = blockIdx.x * per_cta;
     __syncthreads();
-    int r = 0;
+    const int r_end = (blockIdx.x + 1) * per_cta;            // own range; [steal_base, n_reads) is shared by everyone
+    const IdxT primary = (IdxT)ix.primary;
+    const char *occ = reinterpret_cast<const char *>(ix.occ32);
 
-    bool have_read = false, searching = false;
-    int rl = 0, start = 0, p = 0, cw = -1;
+    bool own = true, have_read = false, searching = false;
+    int r = 0, rl = 0, start = 0, p = 0, cw = -1;
+    int64_t wbase = 0;
     uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0;
     IdxT x1 = 0;
     uint32_t st_steps = 0, st_splits = 0;
@@ -123,62 +96,50 @@ k_search(DevIndex ix, SeedLaunch a)
             bool done = false;
             for (;;) {
                 if (!have_read) {
-                    if (q == 0) r = atomicAdd(&s_next, 1);
-                    r = __shfl_sync(gmask, r, 0, 4);
-                    if (r >= r_end) { done = true; break; }
+                    if (own) { r = atomicAdd(&s_next, 1); if (r >= r_end) own = false; }
+                    if (!own) { r = a.steal_base + (int)atomicAdd(a.steal, 1u); if (r >= a.n_reads) { done = true; break; } }
                     rl = a.rlen[r];
-                    stage_read(a.codes, a.dev_off[r], rl, pk, am, q, gmask);
+                    wbase = a.dev_off[r] >> 4;
                     start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
                 }
-                while (start < rl - 13 && ((am[start >> 4] >> (start & 15)) & 1)) start++;
+                while (start < rl - 13) {              // a search cannot start on an ambiguous base
+                    if ((start >> 4) != cw) { cw = start >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+                    if (!((wamb >> (start & 15)) & 1u)) break;
+                    start++;
+                }
                 if (start < rl - 13) break;
-                if (q == 0) { a.nrec[r] = nr; a.nhits[r] = nh; }
+                a.nrec[r] = nr; a.nhits[r] = nh;
                 have_read = false;
             }
             if (done) break;
-            int c0 = (pk[start >> 4] >> ((start & 15) * 2)) & 3;
+            const int c0 = (wcode >> ((start & 15) * 2)) & 3;
             x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
             p = start + 1;
             searching = true;
         }
         bool end = p >= rl;
         if (!end) {
-            if ((p >> 4) != cw) { cw = p >> 4; wcode = pk[cw]; wamb = am[cw]; }
-            end = (wamb >> (p & 15)) & 1;
+            if ((p >> 4) != cw) { cw = p >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+            end = (wamb >> (p & 15)) & 1u;
         }
         if (!end) {
             const IdxT k = x1 - 1, l = k + x2;
             const IdxT kk = k - (k >= primary), ll = l - (l >= primary);
-            // quarter q of block (kk >> 7): byte offset (kk >> 7) * 64 = (kk & ~127) >> 1
-            const ulonglong2 vk = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(kk & ~(IdxT)127) >> 1)));
-            const ulonglong2 vl = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(ll & ~(IdxT)127) >> 1)));
-            const uint32_t code = (wcode >> ((p & 15) * 2)) & 3u;      // c = 3 - code: complement
-            const int c = 3 - (int)code;
-            const uint32_t CH = (code & 2u) ? 0u : ~0u, CL = (code & 1u) ? 0u : ~0u;
-            st_steps++; st_splits += (uint32_t)((kk ^ ll) >> 7 != 0);
-            uint32_t lo, hi;
-            planes32(vk.y, lo, hi);
-            const int eqk = count_eq32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)kk & 127u) - q32))], CH, CL);
-            planes32(vl.y, lo, hi);
-            const int eql = count_eq32(lo, hi, s_mask[max(0, min(32, (int)((uint32_t)ll & 127u) - q32))], CH, CL);
-            uint32_t pc = (uint32_t)eqk | (uint32_t)eql << 16;
-            pc += __shfl_xor_sync(gmask, pc, 1);
-            pc += __shfl_xor_sync(gmask, pc, 2);
-            const uint32_t Dc = __shfl_sync(gmask, (uint32_t)vl.x - (uint32_t)vk.x, c, 4);
-            const IdxT cntk = __shfl_sync(gmask, (IdxT)vk.x, c, 4);
-            const uint32_t EK = pc & 0xffffu, EL = pc >> 16;
-            const uint32_t n2 = Dc + EL - EK;
+            const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3u);     // complement: backward step of revcomp(P)
+            const uint32_t ok = occ_rank(occ, kk, c), ol = occ_rank(occ, ll, c);
+            st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
+            const uint32_t n2 = ol - ok;
             if (n2 == 0) end = true;
             else {
-                x1 = (IdxT)s_L2[c] + 1 + cntk + EK;
+                x1 = (IdxT)s_L2[c] + 1 + ok;
                 x2 = n2;
                 p++;
             }
         }
         if (end) {
-            int len = p - start;
+            const int len = p - start;
             if (x2 <= a.max_dup && len >= 16) { // bwt_search.cpp:173
-                if (q == 0 && (int)nr < a.cap_rec) {
+                if ((int)nr < a.cap_rec) {
                     SearchRec rec; rec.sa_begin = x1; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
                     a.recs[(int64_t)r * a.cap_rec + nr] = rec;
                 }
@@ -188,15 +149,17 @@ k_search(DevIndex ix, SeedLaunch a)
             searching = false;
         }
     }
-    if (q == 0 && st_steps) {
-        atomicAdd(&a.stats->ext_steps, (unsigned long long)st_steps);
-        atomicAdd(&a.stats->ext_blocks, (unsigned long long)st_steps + st_splits);
+    __syncwarp();
+    const unsigned long long ws = warp_sum(st_steps), wp = warp_sum(st_splits);
+    if ((threadIdx.x & 31) == 0 && ws) {
+        atomicAdd(&a.stats->ext_steps, ws);
+        atomicAdd(&a.stats->ext_blocks, ws + wp);
     }
 }
 
-static bool fits32(const DevIndex &ix) { return !ix.force64 && ix.seq_len + 2 < (1ull << 32); }
+static bool fits32(const DevIndex &ix) { return !ix.sa_wide; }
 
-void launch_search(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
+void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
 {
     if (a.n_reads <= 0) return;
     // exactly one wave: as many CTAs as are resident at once (a partial second wave would idle most SMs at the end)
@@ -204,16 +167,20 @@ void launch_search(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k_search<uint32_t>, SEARCH_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_search<uint64_t>, SEARCH_THREADS, 0);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const bool narrow = fits32(ix);
-    int want = (a.n_reads + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
+    int want = (a.n_reads + SEARCH_THREADS - 1) / SEARCH_THREADS;
     int grid = sms * std::max(1, narrow ? occ32 : occ64);
     if (want < grid) grid = want;
-    if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
-    else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a);
+    // 3/4 of the batch is split statically between the CTAs, the last quarter is stolen read by read
+    const int per_cta = (int)((int64_t)a.n_reads * 3 / 4 / grid);
+    a.steal_base = per_cta * grid;
+    cudaMemsetAsync(a.steal, 0, sizeof(uint32_t), st);
+    if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
+    else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -258,26 +225,24 @@ __global__ void k_expand(SeedLaunch a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 2b: SA locate — bwt_sa / bwt_invPsi (bwt_search.cpp:119-137), one group per hit
+// kernel 2b: SA locate — bwt_sa / bwt_invPsi (bwt_search.cpp:119-137), one thread per hit
 // ---------------------------------------------------------------------------------------------------
-// Hits need 0..sa_intv-1 LF steps each (uniformly spread), so a group that walked one hit per pass would idle half the
-// time waiting for the slowest of the warp's 8 groups (round-1 ncu: 12 of 32 lanes active).  Same cure as in k_search:
-// one loop, one LF step per iteration, a group picks up its next hit the moment it finishes one.
-template <typename IdxT>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+// With the full suffix array resident (sa_shift = 0) this is a single gather per hit.  With a sparser array a hit walks
+// LF steps until it reaches a kept entry (geometrically distributed, mean 2^sa_shift - 1): one loop, one LF step per
+// iteration, a lane picks up its next hit the moment it finishes one so the warp stays busy.
+template <typename IdxT, typename SaT>
+__global__ void __launch_bounds__(256)
 k_locate(DevIndex ix, SeedLaunch a, int64_t total)
 {
     __shared__ uint64_t s_L2[5];
-    __shared__ uint32_t s_mask[33];
-    stage_tables(ix, s_L2, s_mask);
-    const int lane = threadIdx.x & 31, q = lane & 3;
-    const unsigned gmask = 0xFu << (lane & ~3);
-    const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_CTA;
+    if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
+    __syncthreads();
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const IdxT primary = (IdxT)ix.primary, sa_mask = (IdxT)ix.sa_mask;
-    const char *occq = reinterpret_cast<const char *>(ix.occ + q);
-    const int q32 = 32 * q - 1;
+    const char *occ = reinterpret_cast<const char *>(ix.occ32);
+    const SaT *sa = reinterpret_cast<const SaT *>(ix.sa);
     unsigned long long st_lf = 0, st_hits = 0;
-    int64_t s = (int64_t)blockIdx.x * GROUPS_PER_CTA + (threadIdx.x >> 2);
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool walking = false;
     IdxT k = 0;
     uint32_t steps = 0;
@@ -288,36 +253,31 @@ k_locate(DevIndex ix, SeedLaunch a, int64_t total)
             steps = 0;
             walking = true;
         }
-        if (k & sa_mask) {                  // one LF step = one block: the symbol at k and its rank come from the same 64 bytes
+        if (k & sa_mask) {                  // one LF step: the symbol at k and its rank come from the same sector
             steps++;
             if (k == primary) k = 0;
             else {
                 const IdxT kk = k - (k > primary);
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(occq + ((uint64_t)(kk & ~(IdxT)127) >> 1)));
-                const int o = (int)((uint32_t)kk & 127u);
-                const int c = __shfl_sync(gmask, symbol_at(v.y, o & 31), o >> 5, 4);
-                const uint32_t CH = (c & 2) ? ~0u : 0u, CL = (c & 1) ? ~0u : 0u;
-                uint32_t lo, hi;
-                planes32(v.y, lo, hi);
-                uint32_t eq = (uint32_t)count_eq32(lo, hi, s_mask[max(0, min(32, o - q32))], CH, CL);
-                eq += __shfl_xor_sync(gmask, eq, 1);
-                eq += __shfl_xor_sync(gmask, eq, 2);
-                const IdxT cnt = __shfl_sync(gmask, (IdxT)v.x, c, 4);
-                k = (IdxT)s_L2[c] + cnt + eq;
+                const char *blk = occ + ((uint64_t)kk >> 6) * 32;
+                const ulonglong2 pl = __ldg(reinterpret_cast<const ulonglong2 *>(blk + 16));
+                const uint32_t t = (uint32_t)kk & 63u;
+                const int c = occ32_symbol(pl.x, pl.y, t);
+                k = (IdxT)s_L2[c] + __ldg(reinterpret_cast<const uint32_t *>(blk) + c) + occ32_eq_upto(pl.x, pl.y, c, t);
             }
         } else {
-            // position of revcomp(P) on the text; P itself starts at the mirrored coordinate 2G - p' - |P|
-            const uint64_t prc = (uint64_t)steps + __ldg(ix.sa + ((uint64_t)k >> ix.sa_shift));
-            if (q == 0) {
-                const uint32_t m = a.meta[s];
-                a.keys[s] = seed_key(2 * (uint64_t)ix.G - prc - (m & 0xFFFF), m >> 16, m & 0xFFFF);
-            }
+            // position of revcomp(P) on the text (entry 0 stands for -1, bwt_index.cpp:31); P itself starts at the
+            // mirrored coordinate 2G - p' - |P|
+            const uint64_t prc = (uint64_t)steps + (k == 0 ? ~0ull : (uint64_t)__ldg(sa + ((uint64_t)k >> ix.sa_shift)));
+            const uint32_t m = a.meta[s];
+            a.keys[s] = seed_key(2 * (uint64_t)ix.G - prc - (m & 0xFFFF), m >> 16, m & 0xFFFF);
             st_lf += steps; st_hits++;
-            s += ngroups;
+            s += nthreads;
             walking = false;
         }
     }
-    if (q == 0 && st_hits) {
+    __syncwarp();
+    st_lf = warp_sum(st_lf); st_hits = warp_sum(st_hits);
+    if ((threadIdx.x & 31) == 0 && st_hits) {
         atomicAdd(&a.stats->lf_steps, st_lf);
         atomicAdd(&a.stats->hits, st_hits);
         atomicAdd(&a.stats->seeds, st_hits);
@@ -330,10 +290,10 @@ void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, int64_t total
     int grid = (a.n_reads + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
     k_expand<<<grid, 256, 0, st>>>(a);
-    int64_t want = (total + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
-    int g2 = (int)(want < 148 * 16 ? want : 148 * 16);
-    if (fits32(ix)) k_locate<uint32_t><<<g2, SEARCH_THREADS, 0, st>>>(ix, a, total);
-    else k_locate<uint64_t><<<g2, SEARCH_THREADS, 0, st>>>(ix, a, total);
+    int64_t want = (total + 255) / 256;
+    int g2 = (int)(want < 148 * 8 ? want : 148 * 8);
+    if (ix.sa_wide) k_locate<uint64_t, uint64_t><<<g2, 256, 0, st>>>(ix, a, total);   // sa_wide <=> 64-bit intervals
+    else k_locate<uint32_t, uint32_t><<<g2, 256, 0, st>>>(ix, a, total);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -36,7 +36,9 @@ def _check_seeds(M, O, reads, max_dup=100):
 
 
 @pytest.mark.parametrize("name,limit", [("c1", 3000), ("c3", 2500), ("c4", 800)])
-def test_seeds_and_candidates_match_oracle(name, limit):
+def test_seeds_and_candidates_match_oracle(name, limit, monkeypatch):
+    # keep the reference's SA sampling (every 32nd entry) so that the device's LF-step counter is the reference's
+    monkeypatch.setenv("DARTGPU_SA_SAMPLE", "32")
     w = workload(name)
     O = po.Oracle(w["idx"])
     M = capi.Mapper(w["idx"])
@@ -56,6 +58,7 @@ def test_64bit_interval_kernels(monkeypatch):
     """Human-sized texts (2G = 6.2e9) need 64-bit SA intervals; the same kernels are instantiated for both widths.
     Force the wide instantiation on a small index and require identical results."""
     monkeypatch.setenv("DARTGPU_FORCE_IDX64", "1")
+    monkeypatch.setenv("DARTGPU_SA_SAMPLE", "32")
     w = workload("c3")
     O = po.Oracle(w["idx"])
     M = capi.Mapper(w["idx"])
@@ -64,6 +67,29 @@ def test_64bit_interval_kernels(monkeypatch):
     _check_seeds(M, O, reads)
     st, oc = M.stats(), O.counters()
     assert (st["ext_steps"], st["ext_blocks"], st["lf_steps"], st["hits"]) == (oc["ext_steps"], oc["ext_blocks"], oc["lf_steps_rc"], oc["hits"])
+    M.close(); O.close()
+
+
+@pytest.mark.parametrize("sample,wide", [(None, False), (1, True), (4, False), (8, True)])
+def test_resident_suffix_array_densities(sample, wide, monkeypatch):
+    """At load the GPU materialises a denser suffix array than the file's every-32nd sampling (the full one by default):
+    the seeds must not depend on the density, and the LF steps walked must shrink accordingly (none for the full SA)."""
+    if sample is not None:
+        monkeypatch.setenv("DARTGPU_SA_SAMPLE", str(sample))
+    if wide:
+        monkeypatch.setenv("DARTGPU_FORCE_IDX64", "1")
+    w = workload("c3")
+    O = po.Oracle(w["idx"])
+    M = capi.Mapper(w["idx"])
+    reads = read_fastq_seqs(w["r1"], 1200)
+    O.reset_counters()
+    _check_seeds(M, O, reads)
+    st, oc = M.stats(), O.counters()
+    assert (st["ext_steps"], st["ext_blocks"], st["hits"]) == (oc["ext_steps"], oc["ext_blocks"], oc["hits"])
+    if sample in (None, 1):
+        assert st["lf_steps"] == 0
+    else:
+        assert 0 < st["lf_steps"] < oc["lf_steps_rc"]
     M.close(); O.close()
 
 

@@ -52,3 +52,11 @@ def test_logic_golden(harness, tmp_path):
         hs, hj = _run(harness, w, (), "logic_" + tag)
         assert _records(hs) == _records(os.path.join(GOLDEN, tag + ".sam"))
         assert open(hj).read() == open(os.path.join(GOLDEN, tag + ".junc")).read()
+
+
+def test_rank_arithmetic_on_the_host():
+    """dart_b200/csrc/rank.cuh (the popcount arithmetic of the search / locate kernels) against a symbol-by-symbol count."""
+    exe = os.path.join(ROOT, "tests", "host", "rank_test")
+    subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "host", "rank_test.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "rank ok" in out
