@@ -77,7 +77,7 @@ EXPORTS = ["dartgpu_default_params", "dartgpu_create", "dartgpu_create_from_file
            "dartgpu_sequence_name", "dartgpu_sequence_length", "dartgpu_set_stream", "dartgpu_seed_and_cluster",
            "dartgpu_kmer_reseed", "dartgpu_nw_align", "dartgpu_map_reads", "dartgpu_get_stats",
            "dartgpu_upload_reads", "dartgpu_seed_and_cluster_resident", "dartgpu_synchronize",
-           "dartgpu_map_reads_resident"]
+           "dartgpu_map_reads_resident", "dartgpu_index_build"]
 
 
 def load_library() -> C.CDLL:
@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
     L.dartgpu_default_params.argtypes = [C.POINTER(Params)]
     L.dartgpu_create_from_files.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.POINTER(Params)]
     L.dartgpu_destroy.argtypes = [C.c_void_p]
+    L.dartgpu_index_build.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_char_p, C.c_uint64]
     L.dartgpu_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
     L.dartgpu_last_error.restype = C.c_char_p
     L.dartgpu_last_error.argtypes = [C.c_void_p]
@@ -252,3 +253,16 @@ class Mapper:
                     reports=_view(out.reports, REPORT, out.n_reports).copy(),
                     cigars=_view(out.cigars, np.uint8, out.n_cigar_bytes).tobytes(),
                     junctions=_view(out.junctions, JUNCTION, out.n_junctions).copy())
+
+
+def index_build(genome, prefix: str, device: int = 0, max_suffixes_per_pass: int = 0) -> None:
+    """`dart index` / bwt_index on the GPU: writes <prefix>.pac/.ann/.amb (the packing bns_fasta2bntseq does,
+    src/BWT_Index/bntseq.c:59-89, :158-211 — host side, linear) and <prefix>.bwt/.sa (dartgpu_index_build).
+    `genome` is a dart_b200.synth.Genome (names + uint8 code arrays, ACGT only)."""
+    from . import synth
+    pac = synth.write_index_meta(prefix, genome)
+    L = load_library()
+    buf = np.ascontiguousarray(pac)
+    rc = L.dartgpu_index_build(device, buf.ctypes.data, int(genome.total_len), prefix.encode(), int(max_suffixes_per_pass))
+    if rc != 0:
+        raise DartGpuError(rc, (L.dartgpu_last_error(None) or b"").decode())

@@ -565,6 +565,18 @@ int dartgpu_create_from_files(dartgpu_ctx **out, int device, const char *prefix,
     return dartgpu_create(out, device, &v, p);
 }
 
+int dartgpu_index_build(int device, const uint8_t *pac, int64_t l_pac, const char *prefix, uint64_t max_suffixes_per_pass)
+{
+    if (!pac || !prefix || l_pac <= 0) return fail(nullptr, DARTGPU_ERR_ARG, "bad argument");
+    return guarded(nullptr, [&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); throw std::make_pair(DARTGPU_ERR_NO_DEVICE, std::string("no CUDA device: libdartgpu has no CPU fallback")); }
+        if (device < 0 || device >= ndev) throw std::make_pair(DARTGPU_ERR_ARG, std::string("device ordinal out of range"));
+        build_index_files(device, pac, l_pac, prefix, max_suffixes_per_pass);
+    });
+}
+
 void dartgpu_destroy(dartgpu_ctx *c)
 {
     if (!c) return;

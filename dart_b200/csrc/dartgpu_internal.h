@@ -103,6 +103,9 @@ void launch_build_ref2(const uint8_t *pac, uint32_t *ref2, int64_t G, cudaStream
 void launch_read_layout(const int64_t *off, int n, int32_t *rlen, uint32_t *padded, cudaStream_t st);
 void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, uint2 *packed, cudaStream_t st);
 
+// index_build.cu
+void build_index_files(int device, const uint8_t *pac, int64_t l_pac, const char *prefix, uint64_t limit);
+
 // seed_kernels.cu
 struct SeedLaunch {
     const uint8_t *codes; const int64_t *dev_off; const int32_t *rlen; int n_reads;

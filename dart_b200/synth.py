@@ -139,6 +139,44 @@ def write_fasta(path: str, g: Genome, width: int = 80) -> None:
                 f.write(chars[full:].tobytes() + b"\n")
 
 
+def pack_2bit(codes: np.ndarray) -> np.ndarray:
+    """4 bases per byte, first base in the top bits (_set_pac, src/BWT_Index/bntseq.c)."""
+    pad = (-len(codes)) % 4
+    if pad:
+        codes = np.concatenate([codes, np.zeros(pad, np.uint8)])
+    c = codes.reshape(-1, 4)
+    return (c[:, 0] << 6 | c[:, 1] << 4 | c[:, 2] << 2 | c[:, 3]).astype(np.uint8)
+
+
+def write_index_meta(prefix: str, g: Genome) -> np.ndarray:
+    """<prefix>.pac / .ann / .amb as the reference's bns_fasta2bntseq(for_only=1) + bns_dump write them
+    (/root/reference/src/BWT_Index/bntseq.c:59-89, :192-205) for an ACGT-only genome. Returns the packed forward strand."""
+    l = g.total_len
+    # contigs are packed back to back: pack the concatenation in slices that start on a multiple of 4 bases
+    packed = np.empty((l + 3) // 4 + 1, dtype=np.uint8)
+    flat = np.concatenate(g.seqs) if len(g.seqs) > 1 else g.seqs[0]
+    step = 1 << 28
+    for a in range(0, l, step):
+        b = min(l, a + step)
+        packed[a // 4:(b + 3) // 4] = pack_2bit(flat[a:b])
+    body = packed[:(l + 3) // 4]
+    with open(prefix + ".pac", "wb") as f:
+        f.write(body.tobytes())
+        if l % 4 == 0:
+            f.write(b"\0")
+        f.write(bytes([l % 4]))
+    with open(prefix + ".ann", "w") as f:
+        f.write(f"{l} {len(g.seqs)} 11\n")
+        off = 0
+        for name, s in zip(g.names, g.seqs):
+            f.write(f"0 {name} (null)\n{off} {len(s)} 0\n")
+            off += len(s)
+    with open(prefix + ".amb", "w") as f:
+        f.write(f"{l} {len(g.seqs)} 0\n")
+    packed[(l + 3) // 4] = 0
+    return packed
+
+
 # ----------------------------------------------------------------------------------------------
 # reads
 # ----------------------------------------------------------------------------------------------

@@ -76,6 +76,12 @@ int  dartgpu_create(dartgpu_ctx **out, int device, const dartgpu_index_view *idx
 /* Convenience: read <prefix>.bwt/.sa/.pac/.ann written by bwt_index / `dart index` / bwa index
  * (formats: src/bwt_index.cpp:15-35, :37-89, :102-121) and call dartgpu_create. */
 int  dartgpu_create_from_files(dartgpu_ctx **out, int device, const char *prefix, const dartgpu_params *p);
+/* Replaces: the BWT / Occ / SA construction of `dart index` / bwt_index (bwa_idx_build steps 2-5,
+ * src/BWT_Index/bwtindex.c:96-144: bwt_bwtgen2, bwt_bwtupdate_core, bwt_cal_sa(32) and the two dumps, src/BWT_Index/bwt.c:174-196).
+ * pac = the forward strand, 2 bits per base, first base in the top bits (what bns_fasta2bntseq leaves in <prefix>.pac,
+ * src/BWT_Index/bntseq.c:158-211), l_pac bases.  Writes <prefix>.bwt and <prefix>.sa byte-identical to the reference's
+ * (the BWT of a text is unique).  max_suffixes_per_pass = 0 sizes the sort passes from the free HBM. */
+int  dartgpu_index_build(int device, const uint8_t *pac, int64_t l_pac, const char *prefix, uint64_t max_suffixes_per_pass);
 void dartgpu_destroy(dartgpu_ctx *ctx);
 int  dartgpu_set_params(dartgpu_ctx *ctx, const dartgpu_params *p);
 const char *dartgpu_last_error(const dartgpu_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
