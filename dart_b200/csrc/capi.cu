@@ -99,7 +99,7 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
     c->d_dev_off.reserve(n + 2); c->d_rlen.reserve(n + 1);
     const int64_t code_bytes = n_bases + 15ll * n + 16;      // upper bound of the padded layout
     c->d_codes.reserve(code_bytes);
-    c->d_packed.reserve(code_bytes / 16 + 1);
+    c->d_packed.reserve(code_bytes / 16 + 4);
     c->n_code_bytes = code_bytes;
     cudaStream_t st = c->stream;
     DG_CUDA(cudaEventRecord(c->ev[0], st));
@@ -341,7 +341,8 @@ static std::string index_key(int device, const dartgpu_index_view *v, int sa_shi
     for (uint64_t i = 0; i < v->n_sa; i += step_s) mix(v->sa[i]);
     for (int i = 0; i < v->n_seqs; i++) mix((uint64_t)v->seq_len_arr[i]);
     char buf[96];
-    snprintf(buf, sizeof buf, "%d:%016llx:%d:%d", device, (unsigned long long)h, sa_shift, (int)force64);
+    const char *kt = getenv("DARTGPU_KTAB");
+    snprintf(buf, sizeof buf, "%d:%016llx:%d:%d:%s", device, (unsigned long long)h, sa_shift, (int)force64, kt ? kt : "auto");
     return buf;
 }
 
@@ -427,6 +428,23 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
         launch_sa_densify(ix, sa_file.p, v->sa_intv, v->n_sa, S->d_sa.p, st);
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaStreamSynchronize(st));
+    }
+    {   // search-start table: K = floor(log4(text length)) - 1 (most K-mers of a read occur), at most 13 (1 GB);
+        // DARTGPU_KTAB=<K> overrides, 0 disables
+        int K = 0;
+        while ((4ull << (2 * K)) <= v->seq_len) K++;          // K = floor(log4(seq_len))
+        K = std::max(4, std::min(13, K - 1));
+        if (const char *e = getenv("DARTGPU_KTAB")) K = std::max(0, std::min(15, atoi(e)));
+        ix.ktab = nullptr; ix.ktab_k = 0;
+        if (K > 0) {
+            DevBuf<KmerStart> tmp;
+            const size_t n_ent = (size_t)1 << (2 * K);
+            S->d_ktab.reserve(n_ent); tmp.reserve(n_ent);
+            launch_build_ktab(ix, K, S->d_ktab.p, tmp.p, st);
+            DG_CUDA(cudaGetLastError());
+            DG_CUDA(cudaStreamSynchronize(st));
+            ix.ktab = S->d_ktab.p; ix.ktab_k = K;
+        }
     }
     {
         DevBuf<uint8_t> dpac;

@@ -23,6 +23,7 @@ struct SharedIndex {
     std::vector<int> end_chr;       // ChrLocMap values
     DevBuf<uint8_t> d_occ32;        // Occ32 blocks
     DevBuf<uint8_t> d_sa;           // u32 or u64 entries
+    DevBuf<KmerStart> d_ktab;       // search-start table
     DevBuf<uint32_t> d_ref2;
     DevBuf<int64_t> d_ends;
     ~SharedIndex();

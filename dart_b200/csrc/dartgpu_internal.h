@@ -22,7 +22,14 @@ namespace dartgpu {
 // (shift 0 = the full suffix array when it fits the memory budget): locate becomes one gather instead of ~31 dependent
 // LF steps per hit.  Entries are u32 when the text length fits 32 bits, u64 otherwise.
 struct Occ32;
+// Search-start table: the SA interval (of the reverse-complemented pattern, as k_search carries it) after the first K
+// bases of a search, for every K-mer, plus the number of those K-1 steps whose two rank queries fall into different
+// 128-symbol BWA blocks (the reference's work counter).  One 16-byte gather replaces K-1 dependent rank steps — on a
+// human-sized index exactly the steps whose two queries land in two random HBM sectors each.
+struct KmerStart { uint64_t x1; uint32_t x2; uint32_t splits; };
 struct DevIndex {
+    const KmerStart *ktab;   // 4^ktab_k entries, k-mer index = first base in the low bits; nullptr when disabled
+    int ktab_k;
     const Occ32 *occ32;      // n_blocks32 blocks (+1 zero guard block)
     uint64_t n_blocks32;
     const void *sa;          // sa[i >> sa_shift] = SA[i] for i % 2^sa_shift == 0; entry 0 is never read (it stands for -1)
@@ -98,6 +105,7 @@ template <class T> struct PinBuf {
 // index_device.cu
 void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *occ, uint64_t n_blocks32, cudaStream_t st);
 // sa_file: the reference's sampled SA (every sa_intv-th entry, entry 0 = -1) on the device; out: every 2^shift-th entry
+void launch_build_ktab(const DevIndex &ix, int K, KmerStart *out, KmerStart *tmp, cudaStream_t st);   // out, tmp: 4^K entries each
 void launch_sa_densify(const DevIndex &ix, const uint64_t *sa_file, uint64_t sa_intv, uint64_t n_sa_file, void *out, cudaStream_t st);
 void launch_build_ref2(const uint8_t *pac, uint32_t *ref2, int64_t G, cudaStream_t st);
 void launch_read_layout(const int64_t *off, int n, int32_t *rlen, uint32_t *padded, cudaStream_t st);

@@ -47,6 +47,44 @@ void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *o
     k_relayout_occ32<<<grid, 256, 0, st>>>(bwt_words, n_words, occ, n_blocks32);
 }
 
+// Search-start table, level by level: entry i of level j+1 = one backward step (k_search's) from entry (i mod 4^j) of
+// level j with read base b = i >> 2j, i.e. BWT symbol c = 3 - b.
+__global__ void k_ktab_level(DevIndex ix, int j, const KmerStart *__restrict__ prev, KmerStart *__restrict__ next)
+{
+    const uint64_t n_next = 1ull << (2 * (j + 1)), pmask = (1ull << (2 * j)) - 1;
+    const char *occ = reinterpret_cast<const char *>(ix.occ32);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_next; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i >> (2 * j));
+        KmerStart e;
+        if (j == 0) { e.x1 = ix.L2[3 - b] + 1; e.x2 = (uint32_t)(ix.L2[b + 1] - ix.L2[b]); e.splits = 0; next[i] = e; continue; }
+        e = prev[i & pmask];
+        if (e.x2 != 0) {
+            const int c = 3 - b;
+            const uint64_t k = e.x1 - 1, l = k + e.x2;
+            const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
+            const Occ32 Bk = *reinterpret_cast<const Occ32 *>(occ + (kk >> 6) * 32), Bl = *reinterpret_cast<const Occ32 *>(occ + (ll >> 6) * 32);
+            const uint32_t ok = Bk.cnt[c] + occ32_eq_upto(Bk.lo, Bk.hi, c, (uint32_t)kk & 63u);
+            const uint32_t ol = Bl.cnt[c] + occ32_eq_upto(Bl.lo, Bl.hi, c, (uint32_t)ll & 63u);
+            e.splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
+            e.x2 = ol - ok;
+            e.x1 = ix.L2[c] + 1 + ok;
+        }
+        next[i] = e;
+    }
+}
+
+void launch_build_ktab(const DevIndex &ix, int K, KmerStart *out, KmerStart *tmp, cudaStream_t st)
+{
+    // ping-pong so that the last level lands in `out`
+    KmerStart *bufs[2] = {(K & 1) ? out : tmp, (K & 1) ? tmp : out};
+    for (int j = 0; j < K; j++) {
+        const uint64_t n_next = 1ull << (2 * (j + 1));
+        uint64_t want = (n_next + 255) / 256;
+        int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+        k_ktab_level<<<grid, 256, 0, st>>>(ix, j, bufs[(j + 1) & 1], bufs[j & 1]);
+    }
+}
+
 // One pass of the LF mapping over the whole text: every entry of the file's sampled SA starts a walker that writes
 // SA[k] = v, steps k -> LF(k), v -> v-1, and stops at the next sampled index (which another walker owns).  Together the
 // walkers visit every SA index exactly once; entries at multiples of 2^shift are kept.  bwt_invPsi:

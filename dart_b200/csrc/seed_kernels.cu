@@ -35,13 +35,25 @@ namespace dartgpu {
 constexpr int SEARCH_THREADS = 128;
 constexpr unsigned FULL = 0xffffffffu;
 
-// Occ(c, kk): occurrences of c in B[0..kk] (kk already adjusted for the primary row), bwt_occ (bwt_search.cpp:43-65)
-__device__ __forceinline__ uint32_t occ_rank(const char *occ, uint64_t kk, int c)
+// One Occ32 block = one 256-bit load (sm_100: LDG.E.256), not cached in L1 (the table is touched at random).  The first
+// version issued a 128-bit load for the planes and a 32-bit load for the count: ncu showed the kernel bound by L1TEX tag
+// throughput (4 fully divergent load instructions per step), so the loads per step were cut to one per distinct block.
+struct OccBlock { uint32_t cnt[4]; uint64_t lo, hi; };
+__device__ __forceinline__ OccBlock load_block(const char *occ, uint64_t blk)
 {
-    const char *blk = occ + (kk >> 6) * 32;
-    const ulonglong2 pl = __ldg(reinterpret_cast<const ulonglong2 *>(blk + 16));
-    const uint32_t cnt = __ldg(reinterpret_cast<const uint32_t *>(blk) + c);
-    return cnt + occ32_eq_upto(pl.x, pl.y, c, (uint32_t)kk & 63u);
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(occ + blk * 32));
+    OccBlock b;
+    b.cnt[0] = r0; b.cnt[1] = r1; b.cnt[2] = r2; b.cnt[3] = r3;
+    b.lo = (uint64_t)r5 << 32 | r4; b.hi = (uint64_t)r7 << 32 | r6;
+    return b;
+}
+// Occ(c, kk): occurrences of c in B[0..kk] (kk already adjusted for the primary row), bwt_occ (bwt_search.cpp:43-65)
+__device__ __forceinline__ uint32_t block_rank(const OccBlock &b, uint32_t t, int c)
+{
+    const uint32_t cnt = (c & 2) ? ((c & 1) ? b.cnt[3] : b.cnt[2]) : ((c & 1) ? b.cnt[1] : b.cnt[0]);
+    return cnt + occ32_eq_upto(b.lo, b.hi, c, t);
 }
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
@@ -83,6 +95,8 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     const int r_end = (blockIdx.x + 1) * per_cta;            // own range; [steal_base, n_reads) is shared by everyone
     const IdxT primary = (IdxT)ix.primary;
     const char *occ = reinterpret_cast<const char *>(ix.occ32);
+    const int K = ix.ktab ? ix.ktab_k : 0;
+    const uint32_t kmask2 = K >= 16 ? ~0u : (1u << (2 * K)) - 1u, kmask1 = (1u << K) - 1u;
 
     bool own = true, have_read = false, searching = false;
     int r = 0, rl = 0, start = 0, p = 0, cw = -1;
@@ -112,9 +126,30 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                 have_read = false;
             }
             if (done) break;
-            const int c0 = (wcode >> ((start & 15) * 2)) & 3;
-            x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
-            p = start + 1;
+            // the first K bases of the search in one gather (KmerStart), when they are all inside the read, unambiguous
+            // and the K-mer occurs; otherwise start from the single base as the reference does
+            bool jumped = false;
+            if (K > 0 && start + K <= rl) {
+                const int sh = start & 15;
+                uint32_t bits = wcode >> (2 * sh), ambs = wamb >> sh;
+                if (sh + K > 16) {
+                    const uint2 w2 = __ldg(a.packed + wbase + cw + 1);
+                    bits |= sh ? w2.x << (32 - 2 * sh) : 0u; ambs |= w2.y << (16 - sh);
+                }
+                if ((ambs & kmask1) == 0) {
+                    const KmerStart e = ix.ktab[bits & kmask2];
+                    if (e.x2 != 0) {
+                        x1 = (IdxT)e.x1; x2 = e.x2; p = start + K;
+                        st_steps += K - 1; st_splits += e.splits;
+                        jumped = true;
+                    }
+                }
+            }
+            if (!jumped) {
+                const int c0 = (wcode >> ((start & 15) * 2)) & 3;
+                x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
+                p = start + 1;
+            }
             searching = true;
         }
         bool end = p >= rl;
@@ -126,7 +161,11 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
             const IdxT k = x1 - 1, l = k + x2;
             const IdxT kk = k - (k >= primary), ll = l - (l >= primary);
             const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3u);     // complement: backward step of revcomp(P)
-            const uint32_t ok = occ_rank(occ, kk, c), ol = occ_rank(occ, ll, c);
+            const uint64_t bk = (uint64_t)kk >> 6, bl = (uint64_t)ll >> 6;
+            const OccBlock Bk = load_block(occ, bk);
+            OccBlock Bl = Bk;
+            if (bl != bk) Bl = load_block(occ, bl);                      // narrow intervals sit in one block: one load
+            const uint32_t ok = block_rank(Bk, (uint32_t)kk & 63u, c), ol = block_rank(Bl, (uint32_t)ll & 63u, c);
             st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
             const uint32_t n2 = ol - ok;
             if (n2 == 0) end = true;
@@ -258,11 +297,10 @@ k_locate(DevIndex ix, SeedLaunch a, int64_t total)
             if (k == primary) k = 0;
             else {
                 const IdxT kk = k - (k > primary);
-                const char *blk = occ + ((uint64_t)kk >> 6) * 32;
-                const ulonglong2 pl = __ldg(reinterpret_cast<const ulonglong2 *>(blk + 16));
+                const OccBlock B = load_block(occ, (uint64_t)kk >> 6);
                 const uint32_t t = (uint32_t)kk & 63u;
-                const int c = occ32_symbol(pl.x, pl.y, t);
-                k = (IdxT)s_L2[c] + __ldg(reinterpret_cast<const uint32_t *>(blk) + c) + occ32_eq_upto(pl.x, pl.y, c, t);
+                const int c = occ32_symbol(B.lo, B.hi, t);
+                k = (IdxT)s_L2[c] + block_rank(B, t, c);
             }
         } else {
             // position of revcomp(P) on the text (entry 0 stands for -1, bwt_index.cpp:31); P itself starts at the

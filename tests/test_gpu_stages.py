@@ -93,6 +93,24 @@ def test_resident_suffix_array_densities(sample, wide, monkeypatch):
     M.close(); O.close()
 
 
+@pytest.mark.parametrize("K,name", [("0", "c1"), ("5", "c4"), ("11", "c3"), ("12", "c5")])
+def test_search_start_table_sizes(K, name, monkeypatch):
+    """The K-mer search-start table (one gather instead of the first K-1 rank steps) must not change a single seed nor
+    the algorithmic work counters, whatever K: absent K-mers, reads shorter than K, ambiguous bases fall back."""
+    monkeypatch.setenv("DARTGPU_KTAB", K)
+    w = workload(name)
+    O = po.Oracle(w["idx"])
+    md = 10000 if name == "c5" else 100
+    M = capi.Mapper(w["idx"], max_dup=md)
+    reads = read_fastq_seqs(w["r1"], 800) + [b"ACGTACGTAC", b"ACGTNACGTACGTTTGACCANNNACGATCAGCTAGCTAGCTAGGGATCGATCGACTAGCTAGCTAGCATCGATCAGCTACGNA", b"N" * 40,
+                                              b"acgtacgtagctagctagctagctagctagcatcgatcagctagctagcta"]
+    O.reset_counters()
+    _check_seeds(M, O, reads, max_dup=md)
+    st, oc = M.stats(), O.counters()
+    assert (st["ext_steps"], st["ext_blocks"], st["hits"]) == (oc["ext_steps"], oc["ext_blocks"], oc["hits"])
+    M.close(); O.close()
+
+
 def test_repeat_rich_genome_with_max_dup_10000():
     w = workload("c5")
     O = po.Oracle(w["idx"])
