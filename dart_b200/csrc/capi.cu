@@ -255,13 +255,13 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
     c->d_kjobs.reserve(n_jobs); c->d_khits.reserve(n_jobs);
     DG_CUDA(cudaMemcpyAsync(c->d_kjobs.p, jobs, (size_t)n_jobs * sizeof(KmerJobDev), cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaEventRecord(c->ev[8], st));
-    launch_kmer(c->ix, codes_dev, c->d_kjobs.p, n_jobs, max_len1, c->d_khits.p, st);
+    launch_kmer(c->ix, codes_dev, c->d_kjobs.p, n_jobs, max_len1, c->d_khits.p, c->kscratch, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[9], st));
     DG_CUDA(cudaMemcpyAsync(c->h_khits.p, c->d_khits.p, (size_t)n_jobs * sizeof(dartgpu_kmer_hit), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
     add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
-    c->stats.kernel_launches += 1;
+    c->stats.kernel_launches += KMER_LAUNCHES;
     c->stats.kmer_jobs += n_jobs;
     for (int i = 0; i < n_jobs; i++) { c->stats.kmer_window_bases += jobs[i].len2; c->stats.kmer_read_bases += jobs[i].len1; }
     c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(KmerJobDev);

@@ -81,6 +81,7 @@ struct dartgpu_ctx {
     dartgpu::PinBuf<dartgpu::KmerJobDev> h_kjobs;
     dartgpu::DevBuf<dartgpu::KmerJobDev> d_kjobs;
     dartgpu::DevBuf<dartgpu_kmer_hit> d_khits;
+    dartgpu::KmerScratch kscratch;
     dartgpu::PinBuf<dartgpu_kmer_hit> h_khits;
     dartgpu::PinBuf<dartgpu::NwJobDev> h_njobs;
     dartgpu::DevBuf<dartgpu::NwJobDev> d_njobs;

@@ -144,7 +144,14 @@ int nw_grid_warps();
 
 // kmer_kernel.cu
 struct KmerJobDev { int64_t s1_off; int64_t gpos; int32_t len1, len2; };
+struct KmerScratch {       // device scratch of the k-mer fast path, owned by the context
+    DevBuf<uint32_t> ntiles, cap, count, recs, heavy_list, heavy_count;
+    DevBuf<int64_t> tile_off, rec_off;
+    DevBuf<uint8_t> scan_tmp;
+    PinBuf<int64_t> h_total;
+};
+constexpr int KMER_LAUNCHES = 6;   // prep, 2 scans (counted as one each), scan, walk, ring
 void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *jobs, int n_jobs, int max_len1,
-                 dartgpu_kmer_hit *out, cudaStream_t st);
+                 dartgpu_kmer_hit *out, KmerScratch &scratch, cudaStream_t st);
 
 } // namespace dartgpu

@@ -21,6 +21,8 @@
 // Quirks kept (only reachable with non-ACGT read symbols): only a literal 'N' breaks an 8-mer; other symbols
 // add 4 into the rolling id; the first id after a (re)start is unmasked; after an 'N' restart the rolling
 // window is one base late (KmerAnalysis.cpp:52, :60-75).  Those fragments take a sequential path on thread 0.
+#include <cstdlib>
+
 #include "dartgpu_internal.h"
 
 namespace dartgpu {
@@ -41,7 +43,8 @@ __device__ __forceinline__ uint32_t genome_kmer(const DevIndex &ix, int64_t p)
 }
 
 __global__ void __launch_bounds__(KMER_THREADS)
-k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, int n_jobs,
+k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs,
+       const uint32_t *__restrict__ job_list, const uint32_t *__restrict__ n_listed,
        int tab_cap, int ring, dartgpu_kmer_hit *out)
 {
     extern __shared__ uint32_t smem[];
@@ -53,7 +56,9 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
     __shared__ int s_nk, s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const int n_list = (int)*n_listed;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int job = (int)job_list[li];
         const KmerJobDev J = jobs[job];
         const int L1 = J.len1, L2 = J.len2;
         int best_r = 0, best_g = 0, best_len = 0;
@@ -200,20 +205,212 @@ k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restr
 
 static int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
+// =====================================================================================================
+// Fast path: windows scanned by the whole grid, matches kept as records
+// =====================================================================================================
+// Round-1 profile (config[2] at full size: 16 k jobs / 1 M reads, windows of 37 kb on average, up to 500 kb): the
+// block-per-job kernel above spends its time in the three block barriers and the diagonal retirement of every 1024-position
+// tile (~6 us per tile, 75x off the kernel's memory roofline), and a 500 kb window is walked by a single CTA.  But a
+// window position matches one of the gap's ~100 8-mers with probability ~0.15 %, so the matches themselves are few:
+//   k_kmer_prep   one thread per job: classify, count 4096-position tiles and the record capacity of the job;
+//   k_kmer_scan   the grid walks the flattened tile space of ALL jobs (a long window is spread over many CTAs); a thread
+//                 forms 16 consecutive 8-mers from three coalesced words, tests them against a 64 Kbit bitmap of the gap's
+//                 8-mers and resolves the rare hits through a small hash table; every match becomes one 32-bit record
+//                 (diagonal << 10 | read position) in the job's slice of a record pool — no barrier per tile;
+//   k_kmer_walk   one CTA per job sorts its records (a few hundred) and walks the diagonals in increasing order with the
+//                 reference's carried counter `s` (KmerAnalysis.cpp:147-163) — the same arithmetic as the ring kernel.
+// Jobs the fast path does not take — non-ACGT symbols in the gap (the N quirks), more matches than the job's capacity
+// (low-complexity gaps), windows beyond 2^22 — go through the ring kernel above, which has no such limits.
+constexpr int KS_THREADS = 256, KS_PPT = 16, KS_TILE = KS_THREADS * KS_PPT, KS_CHUNK = 4;
+constexpr int KS_HASH = 2048;                    // >= 2 x the most 8-mers a gap can have (DARTGPU_MAX_RLEN - 7)
+constexpr uint32_t KS_CAP_MAX = 4096, KS_EMPTY = 0xFFFFFFFFu;
+
+__global__ void k_kmer_prep(const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, int n_jobs, int tab_cap, uint32_t cap_max,
+                            uint32_t *ntiles, uint32_t *cap, uint32_t *count, uint32_t *heavy_list, uint32_t *heavy_count,
+                            dartgpu_kmer_hit *out)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= n_jobs; j += gridDim.x * blockDim.x) {
+        if (j == n_jobs) { ntiles[j] = 0; cap[j] = 0; continue; }
+        const KmerJobDev J = jobs[j];
+        const int L1 = J.len1, L2 = J.len2;
+        uint32_t nt = 0, cp = 0;
+        if (L1 >= 8 && L2 >= 8 && L1 <= tab_cap) {
+            bool plain = L1 <= DARTGPU_MAX_RLEN && (int64_t)L1 + L2 < (1 << 22);
+            const uint8_t *s1 = codes + J.s1_off;
+            for (int p = 0; p < L1 && plain; p++) plain = (s1[p] & 4) == 0;
+            const uint64_t expect = ((uint64_t)(L2 - 7) * (uint64_t)(L1 - 7)) >> 16;     // chance matches
+            uint64_t want = 2 * expect + 2 * (uint64_t)L1 + 64;
+            if (cap_max < KS_CAP_MAX && want > cap_max) want = cap_max;      // test hook: force overflows into the ring kernel
+            if (plain && want <= KS_CAP_MAX) { nt = (uint32_t)((L2 - 7 + KS_TILE - 1) / KS_TILE); cp = (uint32_t)want; }
+            else heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)j;
+        } else { out[j].rpos = 0; out[j].gpos = 0; out[j].len = 0; }
+        ntiles[j] = nt; cap[j] = cp; count[j] = 0;
+    }
+}
+
+__device__ __forceinline__ uint32_t ks_hash(uint32_t id) { return ((id * 40503u) >> 4) & (KS_HASH - 1); }
+
+__global__ void __launch_bounds__(KS_THREADS)
+k_kmer_scan(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, int n_jobs,
+            const int64_t *__restrict__ tile_off, const int64_t *__restrict__ rec_off, const uint32_t *__restrict__ cap,
+            uint32_t *count, uint32_t *recs)
+{
+    __shared__ uint32_t bm[2048];
+    __shared__ uint32_t ht[KS_HASH];
+    __shared__ int s_job;
+    const int tid = threadIdx.x;
+    const int64_t total = tile_off[n_jobs];
+    const int64_t nchunks = (total + KS_CHUNK - 1) / KS_CHUNK;
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t t0 = ch * KS_CHUNK, t1 = min(total, t0 + KS_CHUNK);
+        __syncthreads();
+        if (tid == 0) {                      // the job that owns tile t0: last j with tile_off[j] <= t0
+            int lo = 0, hi = n_jobs;
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tile_off[mid] <= t0) lo = mid; else hi = mid - 1; }
+            s_job = lo;
+        }
+        __syncthreads();
+        int job = s_job;
+        int64_t t = t0;
+        while (t < t1) {
+            while (tile_off[job + 1] <= t) job++;            // skips jobs without tiles
+            const KmerJobDev J = jobs[job];
+            const int L1 = J.len1, ngk = J.len2 - 7;
+            // ---- the gap's 8-mers: presence bitmap + hash table (id << 16 | read position) ----
+            __syncthreads();
+            for (int i = tid; i < 2048; i += KS_THREADS) bm[i] = 0;
+            for (int i = tid; i < KS_HASH; i += KS_THREADS) ht[i] = KS_EMPTY;
+            __syncthreads();
+            const uint8_t *s1 = codes + J.s1_off;
+            for (int p = tid; p < L1 - 7; p += KS_THREADS) {
+                uint32_t id = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) id = (id << 2) | (s1[p + i] & 3u);
+                atomicOr(&bm[id >> 5], 1u << (id & 31));
+                uint32_t slot = ks_hash(id);
+                while (atomicCAS(&ht[slot], KS_EMPTY, id << 16 | (uint32_t)p) != KS_EMPTY) slot = (slot + 1) & (KS_HASH - 1);
+            }
+            __syncthreads();
+            const int64_t t_end = min(t1, tile_off[job + 1]);
+            const uint32_t my_cap = cap[job];
+            uint32_t *my_recs = recs + rec_off[job];
+            for (; t < t_end; t++) {
+                const int g_first = (int)(t - tile_off[job]) * KS_TILE + tid * KS_PPT;
+                if (g_first >= ngk) continue;
+                const int64_t q0 = J.gpos + g_first;
+                const uint32_t *w = ix.ref2 + (q0 >> 4);
+                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                const uint64_t x01 = (uint64_t)w0 << 32 | w1, x12 = (uint64_t)w1 << 32 | w2;
+                const int o0 = (int)(q0 & 15);
+#pragma unroll
+                for (int i = 0; i < KS_PPT; i++) {
+                    const int off = o0 + i;
+                    const uint64_t x = off < 16 ? x01 : x12;
+                    const uint32_t id = (uint32_t)(x >> (48 - 2 * (off & 15))) & 0xFFFFu;
+                    if (g_first + i < ngk && ((bm[id >> 5] >> (id & 31)) & 1u)) {
+                        uint32_t slot = ks_hash(id), e;
+                        while ((e = ht[slot]) != KS_EMPTY) {
+                            if ((e >> 16) == id) {
+                                const uint32_t r = e & 0xFFFFu;
+                                const uint32_t dd = (uint32_t)(g_first + i - (int)r + L1);
+                                const uint32_t k = atomicAdd(&count[job], 1u);
+                                if (k < my_cap) my_recs[k] = dd << 10 | r;
+                            }
+                            slot = (slot + 1) & (KS_HASH - 1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_kmer_walk(const KmerJobDev *__restrict__ jobs, int n_jobs, const int64_t *__restrict__ rec_off, const uint32_t *__restrict__ cap,
+            const uint32_t *__restrict__ count, const uint32_t *__restrict__ recs, uint32_t *heavy_list, uint32_t *heavy_count,
+            dartgpu_kmer_hit *out)
+{
+    __shared__ uint32_t sm[KS_CAP_MAX];
+    const int tid = threadIdx.x;
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const uint32_t cp = cap[job];
+        if (cp == 0) continue;                                   // not a fast-path job
+        const uint32_t n = count[job];
+        if (n > cp) { if (tid == 0) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)job; continue; }
+        int N = 32;
+        while (N < (int)n) N <<= 1;
+        __syncthreads();
+        const uint32_t *src = recs + rec_off[job];
+        for (int i = tid; i < N; i += 128) sm[i] = i < (int)n ? src[i] : 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = 2; k <= N; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < N; i += 128) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const uint32_t x = sm[i], y = sm[p];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { sm[i] = y; sm[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid == 0) {
+            const int L1 = jobs[job].len1;
+            int best_r = 0, best_g = 0, best_len = 0, s_acc = 1, max_len = 0;
+            uint32_t i = 0;
+            while (i < n) {                                      // one run of equal PosDiff: records sorted by read position
+                const uint32_t dd = sm[i] >> 10;
+                const int mn = (int)(sm[i] & 1023u);
+                uint32_t e = i + 1;
+                while (e < n && (sm[e] >> 10) == dd) e++;
+                const int mx = (int)(sm[e - 1] & 1023u);
+                s_acc += (int)(e - i) - 1;
+                const int l = 8 + (mx - mn);
+                if (l > max_len && s_acc > (l - 8) / 2) {
+                    best_r = mn; best_g = mn + ((int)dd - L1); best_len = l;
+                    max_len = l; s_acc = 1;
+                }
+                i = e;
+            }
+            out[job].rpos = best_r; out[job].gpos = best_g; out[job].len = best_len;
+        }
+    }
+}
+
+
 void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *jobs, int n_jobs, int max_len1,
-                 dartgpu_kmer_hit *out, cudaStream_t st)
+                 dartgpu_kmer_hit *out, KmerScratch &S, cudaStream_t st)
 {
     if (n_jobs <= 0) return;
-    int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
-    int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
-    size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8 + 2048) * 4;
+    const int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
+    S.ntiles.reserve(n_jobs + 2); S.cap.reserve(n_jobs + 2); S.count.reserve(n_jobs + 2);
+    S.tile_off.reserve(n_jobs + 2); S.rec_off.reserve(n_jobs + 2);
+    S.heavy_list.reserve(n_jobs + 2); S.heavy_count.reserve(4); S.h_total.reserve(2);
+    const size_t tmp = scan_tmp_bytes(n_jobs);
+    S.scan_tmp.reserve(tmp + 256);
+    DG_CUDA(cudaMemsetAsync(S.heavy_count.p, 0, sizeof(uint32_t), st));
+    int g1 = (n_jobs + 1 + 255) / 256; if (g1 > 148 * 8) g1 = 148 * 8;
+    const uint32_t cap_max = getenv("DARTGPU_KMER_CAP") ? (uint32_t)atoi(getenv("DARTGPU_KMER_CAP")) : KS_CAP_MAX;
+    k_kmer_prep<<<g1, 256, 0, st>>>(codes, jobs, n_jobs, tab_cap, cap_max, S.ntiles.p, S.cap.p, S.count.p, S.heavy_list.p, S.heavy_count.p, out);
+    launch_scan_u32_to_i64(S.ntiles.p, S.tile_off.p, n_jobs, S.scan_tmp.p, tmp, st);
+    launch_scan_u32_to_i64(S.cap.p, S.rec_off.p, n_jobs, S.scan_tmp.p, tmp, st);
+    DG_CUDA(cudaMemcpyAsync(S.h_total.p, S.rec_off.p + n_jobs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    S.recs.reserve((size_t)S.h_total.p[0] + 1);
+    k_kmer_scan<<<148 * 8, KS_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, S.tile_off.p, S.rec_off.p, S.cap.p, S.count.p, S.recs.p);
+    k_kmer_walk<<<n_jobs < 148 * 16 ? n_jobs : 148 * 16, 128, 0, st>>>(jobs, n_jobs, S.rec_off.p, S.cap.p, S.count.p, S.recs.p,
+                                                                      S.heavy_list.p, S.heavy_count.p, out);
+    // whatever the fast path declined: the ring kernel, reading the list's length on the device
+    const int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
+    const size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8 + 2048) * 4;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    int grid = n_jobs < 148 * 8 ? n_jobs : 148 * 8;
-    k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, n_jobs, tab_cap, ring, out);
+    const int grid = n_jobs < 148 * 4 ? n_jobs : 148 * 4;
+    k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, S.heavy_list.p, S.heavy_count.p, tab_cap, ring, out);
 }
 
 } // namespace dartgpu

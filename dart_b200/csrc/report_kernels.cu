@@ -70,9 +70,9 @@ __global__ void k_set_sv_off(int64_t ncand, CandState *cs, const int64_t *off)
 
 // One thread per candidate.  The candidate's record is worked on in registers and its seeds, when few (the normal
 // case: 1-4 seeds), in a shared-memory slot; larger candidates work in place on their HBM slice.
-constexpr int STAGE_SEEDS = 8;
+constexpr int STAGE_SEEDS = 5;
 template <int WHICH>
-__global__ void __launch_bounds__(TPB) k_phase(Env E, int64_t ncand)
+__global__ void __launch_bounds__(TPB, 8) k_phase(Env E, int64_t ncand)
 {
     __shared__ RSeed s_slot[TPB * STAGE_SEEDS];
     for (int64_t cid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cid < ncand; cid += (int64_t)gridDim.x * blockDim.x) {
@@ -358,12 +358,12 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     if (nk > 0) {
         DG_CUDA(cudaEventRecord(c->ev[8], st));
         k_kmer_work<<<grid_for(nk), TPB, 0, st>>>(D->kjobs.p, nk, D->work.p);
-        launch_kmer(c->ix, c->d_codes.p, D->kjobs.p, nk, std::max(c->max_rlen, 8), D->khits.p, st);
+        launch_kmer(c->ix, c->d_codes.p, D->kjobs.p, nk, std::max(c->max_rlen, 8), D->khits.p, c->kscratch, st);
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaEventRecord(c->ev[9], st));
         DG_CUDA(cudaStreamSynchronize(st));
         add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
-        c->stats.kernel_launches += 1;
+        c->stats.kernel_launches += KMER_LAUNCHES;
     }
     c->stats.kmer_jobs += nk;
 

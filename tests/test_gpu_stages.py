@@ -236,7 +236,12 @@ def test_nw_golden(golden):
     M.close(); O.close()
 
 
-def test_kmer_matches_oracle():
+@pytest.mark.parametrize("cap", [None, "40"])
+def test_kmer_matches_oracle(cap, monkeypatch):
+    """Both k-mer paths: the grid-wide scan that keeps matches as records, and (cap=40: nearly every job overflows its
+    record capacity; N / IUPAC symbols; the 300 kb windows when their capacity would exceed the limit) the ring kernel."""
+    if cap:
+        monkeypatch.setenv("DARTGPU_KMER_CAP", cap)
     w = workload("c5")                                        # repeat-rich: many equal-PosDiff runs
     O = po.Oracle(w["idx"])
     M = capi.Mapper(w["idx"])
@@ -247,10 +252,12 @@ def test_kmer_matches_oracle():
         jobs.append((len(frags), len(f1), gpos, glen))
         frags.extend(f1)
         expect.append(O.kmer_pair(f1, _win(O, gpos, glen)))
-    for _ in range(1500):
+    for it in range(1500):
         glen = rng.choice([rng.randint(26, 300), rng.randint(300, 6000), rng.randint(6000, 60000)])
+        if it % 100 == 7:
+            glen = rng.randint(200000, 500000)
         gpos = rng.randint(0, 2 * G - glen - 1)
-        L1 = rng.randint(21, 101)
+        L1 = rng.randint(21, 101) if it % 10 else rng.randint(101, 250)
         mode = rng.random()
         if mode < 0.7 and glen > L1 + 2:
             p = rng.randint(0, glen - L1 - 1)
