@@ -186,7 +186,7 @@ def workload_config(sample_pairs=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
@@ -238,17 +238,22 @@ def main():
         subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]], (off - off[0]).copy()))
     pool = ThreadPoolExecutor(CONTEXTS)
 
-    def step(resident):
-        futs = [pool.submit(m.map_reads, sb, resident, False) for m, sb in zip(mappers, subs)]
+    def run_steps(resident, steps):
+        """`steps` passes over the batch.  Every context maps its own slice `steps` times back to back; the contexts are
+        not re-synchronised between steps (a barrier per step would run them in lockstep: all in their kernels, then all
+        in their D2H, and nothing would overlap), only at the two ends of the timed region."""
+        def worker(m, sb):
+            for _ in range(steps):
+                m.map_reads(sb, resident, False)
+        futs = [pool.submit(worker, m, sb) for m, sb in zip(mappers, subs)]
         for f in futs:
             f.result()
 
-    def timed(fn, steps):
+    def timed(resident, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        run_steps(resident, steps)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -259,14 +264,13 @@ def main():
     # ---- device-resident arm ----
     for m, sb in zip(mappers, subs):
         m.upload_reads(sb)
-    for _ in range(args.warmup):
-        step(True)
+    run_steps(True, args.warmup)
     sampler = ClockSampler(local); sampler.start()
-    ms_res = timed(lambda: step(True), args.steps)
+    ms_res = timed(True, args.steps)
     sts = [m.stats() for m in mappers]
     # ---- end-to-end arm (host buffers in, host results out) ----
-    step(False)
-    ms_e2e = timed(lambda: step(False), args.steps)
+    run_steps(False, max(1, args.warmup // 2))
+    ms_e2e = timed(False, args.steps)
     sts_e2e = [m.stats() for m in mappers]
     clocks = sampler.result()
     st = {k: sum(x[k] for x in sts) for k in sts[0]}          # work and kernel time summed over the contexts of this rank

@@ -95,7 +95,7 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
     c->h_raw.reserve(n_bases + 16); c->h_off.reserve(n + 2);
     c->n_reads = n; c->max_rlen = max_rlen;
     c->cap_rec = std::max(1, (max_rlen + 15) / 16);
-    c->d_raw.reserve(n_bases + 16); c->d_off.reserve(n + 2); c->d_padded.reserve(n + 2);
+    c->d_raw.reserve(n_bases + 32); c->d_off.reserve(n + 2); c->d_padded.reserve(n + 2);
     c->d_dev_off.reserve(n + 2); c->d_rlen.reserve(n + 1);
     const int64_t code_bytes = n_bases + 15ll * n + 16;      // upper bound of the padded layout
     c->d_codes.reserve(code_bytes);
@@ -293,14 +293,14 @@ void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs
     c->h_nw_ops.reserve(ops_total + 1); c->h_nw_nops.reserve(n_jobs);
     DG_CUDA(cudaMemcpyAsync(c->d_njobs.p, jobs, (size_t)n_jobs * sizeof(NwJobDev), cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaEventRecord(c->ev[10], st));
-    launch_nw(c->ix, codes_dev, c->d_njobs.p, n_jobs, c->d_nw_flags.p, c->d_nw_rowbuf.p, rb_per_warp, c->d_nw_ops.p, c->d_nw_nops.p, st);
+    launch_nw(c->ix, codes_dev, c->d_njobs.p, n_jobs, c->d_nw_flags.p, c->d_nw_rowbuf.p, rb_per_warp, c->d_nw_ops.p, c->d_nw_nops.p, c->nwscratch, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[11], st));
     DG_CUDA(cudaMemcpyAsync(c->h_nw_ops.p, c->d_nw_ops.p, ops_total, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(c->h_nw_nops.p, c->d_nw_nops.p, (size_t)n_jobs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
     add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
-    c->stats.kernel_launches += 1;
+    c->stats.kernel_launches += NW_LAUNCHES;
     c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(NwJobDev);
     c->stats.d2h_bytes += ops_total + (uint64_t)n_jobs * 4;
     for (int i = 0; i < n_jobs; i++) c->o_op_off[i + 1] = c->o_op_off[i] + c->h_nw_nops.p[i];

@@ -82,6 +82,7 @@ struct dartgpu_ctx {
     dartgpu::DevBuf<dartgpu::KmerJobDev> d_kjobs;
     dartgpu::DevBuf<dartgpu_kmer_hit> d_khits;
     dartgpu::KmerScratch kscratch;
+    dartgpu::NwScratch nwscratch;
     dartgpu::PinBuf<dartgpu_kmer_hit> h_khits;
     dartgpu::PinBuf<dartgpu::NwJobDev> h_njobs;
     dartgpu::DevBuf<dartgpu::NwJobDev> d_njobs;

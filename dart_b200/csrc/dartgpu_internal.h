@@ -138,8 +138,13 @@ void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, 
 
 // nw_kernel.cu
 struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int64_t aux_off; int32_t m, n; };
+struct NwScratch {         // sort buffers of the thread-per-job NW class, owned by the context
+    DevBuf<uint32_t> keys, vals, keys2, vals2;
+    DevBuf<uint8_t> tmp;
+};
+constexpr int NW_LAUNCHES = 4;     // sort keys, radix sort (counted once), k_nw_thread, k_nw
 void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,
-               uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, cudaStream_t st);
+               uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, NwScratch &scratch, cudaStream_t st);
 int nw_grid_warps();
 
 // kmer_kernel.cu

@@ -188,27 +188,40 @@ __global__ void k_encode_reads(const uint8_t *__restrict__ raw, const int64_t *_
         tab[i] = v;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    // 8 lanes per read (a 101-base read has 7 chunks of 16 bases; the first version gave it a whole warp), one chunk per
+    // lane: five aligned 32-bit loads cover the 16 unaligned source bytes, funnel shifts realign them.
+    const int gl = threadIdx.x & 7;
+    const int ngroups = (gridDim.x * blockDim.x) >> 3;
     const int64_t base0 = off[0];
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += nwarps) {
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n; r += ngroups) {
         const int64_t src = off[r] - base0;
         const int rl = (int)(off[r + 1] - off[r]);
         const int chunks = (rl + 15) >> 4;
-        uint4 *dst = reinterpret_cast<uint4 *>(codes + dev_off[r]);
-        for (int ch = lane; ch < chunks; ch += 32) {
+        const int64_t d0 = dev_off[r];
+        uint4 *dst = reinterpret_cast<uint4 *>(codes + d0);
+        for (int ch = gl; ch < chunks; ch += 8) {
+            const int64_t s0 = src + 16 * ch;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(raw + (s0 & ~(int64_t)3));
+            const int sh = (int)(s0 & 3) * 8;
+            uint32_t in[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) in[k] = wp[k];
             uint32_t w[4] = {0, 0, 0, 0};
             uint32_t two = 0, amb = 0;      // the search kernel's view: 2 bits per base + one "not ACGT" bit
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int p = ch * 16 + k;
-                uint32_t c = p < rl ? tab[raw[src + p]] : 4u;
-                w[k >> 2] |= c << (8 * (k & 3));
-                two |= (c & 3u) << (2 * k);
-                amb |= ((c >> 2) & 1u) << k;
+            for (int q = 0; q < 4; q++) {
+                const uint32_t x = __funnelshift_r(in[q], in[q + 1], sh);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = ch * 16 + q * 4 + k;
+                    const uint32_t c = p < rl ? tab[(x >> (8 * k)) & 0xFFu] : 4u;
+                    w[q] |= c << (8 * k);
+                    two |= (c & 3u) << (2 * (q * 4 + k));
+                    amb |= ((c >> 2) & 1u) << (q * 4 + k);
+                }
             }
             dst[ch] = make_uint4(w[0], w[1], w[2], w[3]);
-            packed[(dev_off[r] >> 4) + ch] = make_uint2(two, amb);
+            packed[(d0 >> 4) + ch] = make_uint2(two, amb);
         }
     }
 }
@@ -220,7 +233,7 @@ void launch_read_layout(const int64_t *off, int n, int32_t *rlen, uint32_t *padd
 }
 void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, uint2 *packed, cudaStream_t st)
 {
-    int64_t want = ((int64_t)n * 32 + 255) / 256;
+    int64_t want = ((int64_t)n * 8 + 255) / 256;
     int grid = (int)(want < 148 * 16 ? want : 148 * 16); if (grid < 1) grid = 1;
     k_encode_reads<<<grid, 256, 0, st>>>(raw, off, dev_off, n, codes, packed);
 }

@@ -212,7 +212,7 @@ static int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 // block-per-job kernel above spends its time in the three block barriers and the diagonal retirement of every 1024-position
 // tile (~6 us per tile, 75x off the kernel's memory roofline), and a 500 kb window is walked by a single CTA.  But a
 // window position matches one of the gap's ~100 8-mers with probability ~0.15 %, so the matches themselves are few:
-//   k_kmer_prep   one thread per job: classify, count 4096-position tiles and the record capacity of the job;
+//   k_kmer_prep   one thread per job: classify, count the chunks (up to 32 tiles of 4096 positions) and the record capacity of the job;
 //   k_kmer_scan   the grid walks the flattened tile space of ALL jobs (a long window is spread over many CTAs); a thread
 //                 forms 16 consecutive 8-mers from three coalesced words, tests them against a 64 Kbit bitmap of the gap's
 //                 8-mers and resolves the rare hits through a small hash table; every match becomes one 32-bit record
@@ -221,7 +221,7 @@ static int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 //                 reference's carried counter `s` (KmerAnalysis.cpp:147-163) — the same arithmetic as the ring kernel.
 // Jobs the fast path does not take — non-ACGT symbols in the gap (the N quirks), more matches than the job's capacity
 // (low-complexity gaps), windows beyond 2^22 — go through the ring kernel above, which has no such limits.
-constexpr int KS_THREADS = 256, KS_PPT = 16, KS_TILE = KS_THREADS * KS_PPT, KS_CHUNK = 4;
+constexpr int KS_THREADS = 256, KS_PPT = 16, KS_TILE = KS_THREADS * KS_PPT, KS_CHUNK = 32;
 constexpr int KS_HASH = 2048;                    // >= 2 x the most 8-mers a gap can have (DARTGPU_MAX_RLEN - 7)
 constexpr uint32_t KS_CAP_MAX = 4096, KS_EMPTY = 0xFFFFFFFFu;
 
@@ -241,7 +241,7 @@ __global__ void k_kmer_prep(const uint8_t *__restrict__ codes, const KmerJobDev 
             const uint64_t expect = ((uint64_t)(L2 - 7) * (uint64_t)(L1 - 7)) >> 16;     // chance matches
             uint64_t want = 2 * expect + 2 * (uint64_t)L1 + 64;
             if (cap_max < KS_CAP_MAX && want > cap_max) want = cap_max;      // test hook: force overflows into the ring kernel
-            if (plain && want <= KS_CAP_MAX) { nt = (uint32_t)((L2 - 7 + KS_TILE - 1) / KS_TILE); cp = (uint32_t)want; }
+            if (plain && want <= KS_CAP_MAX) { nt = (uint32_t)((L2 - 7 + KS_TILE * KS_CHUNK - 1) / (KS_TILE * KS_CHUNK)); cp = (uint32_t)want; }
             else heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)j;
         } else { out[j].rpos = 0; out[j].gpos = 0; out[j].len = 0; }
         ntiles[j] = nt; cap[j] = cp; count[j] = 0;
@@ -252,62 +252,65 @@ __device__ __forceinline__ uint32_t ks_hash(uint32_t id) { return ((id * 40503u)
 
 __global__ void __launch_bounds__(KS_THREADS)
 k_kmer_scan(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, int n_jobs,
-            const int64_t *__restrict__ tile_off, const int64_t *__restrict__ rec_off, const uint32_t *__restrict__ cap,
+            const int64_t *__restrict__ chunk_off, const int64_t *__restrict__ rec_off, const uint32_t *__restrict__ cap,
             uint32_t *count, uint32_t *recs)
 {
     __shared__ uint32_t bm[2048];
     __shared__ uint32_t ht[KS_HASH];
     __shared__ int s_job;
     const int tid = threadIdx.x;
-    const int64_t total = tile_off[n_jobs];
-    const int64_t nchunks = (total + KS_CHUNK - 1) / KS_CHUNK;
+    const int64_t nchunks = chunk_off[n_jobs];
+    // a chunk = up to KS_CHUNK consecutive tiles of ONE job, so the gap's tables are built once per chunk
     for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const int64_t t0 = ch * KS_CHUNK, t1 = min(total, t0 + KS_CHUNK);
         __syncthreads();
-        if (tid == 0) {                      // the job that owns tile t0: last j with tile_off[j] <= t0
+        if (tid == 0) {                      // the job that owns chunk ch: last j with chunk_off[j] <= ch
             int lo = 0, hi = n_jobs;
-            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tile_off[mid] <= t0) lo = mid; else hi = mid - 1; }
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_off[mid] <= ch) lo = mid; else hi = mid - 1; }
             s_job = lo;
         }
+        for (int i = tid; i < 2048; i += KS_THREADS) bm[i] = 0;
+        for (int i = tid; i < KS_HASH; i += KS_THREADS) ht[i] = KS_EMPTY;
         __syncthreads();
-        int job = s_job;
-        int64_t t = t0;
-        while (t < t1) {
-            while (tile_off[job + 1] <= t) job++;            // skips jobs without tiles
-            const KmerJobDev J = jobs[job];
-            const int L1 = J.len1, ngk = J.len2 - 7;
-            // ---- the gap's 8-mers: presence bitmap + hash table (id << 16 | read position) ----
-            __syncthreads();
-            for (int i = tid; i < 2048; i += KS_THREADS) bm[i] = 0;
-            for (int i = tid; i < KS_HASH; i += KS_THREADS) ht[i] = KS_EMPTY;
-            __syncthreads();
-            const uint8_t *s1 = codes + J.s1_off;
-            for (int p = tid; p < L1 - 7; p += KS_THREADS) {
-                uint32_t id = 0;
+        const int job = s_job;
+        const KmerJobDev J = jobs[job];
+        const int L1 = J.len1, ngk = J.len2 - 7;
+        // ---- the gap's 8-mers: presence bitmap + hash table (id << 16 | read position) ----
+        const uint8_t *s1 = codes + J.s1_off;
+        for (int p = tid; p < L1 - 7; p += KS_THREADS) {
+            uint32_t id = 0;
 #pragma unroll
-                for (int i = 0; i < 8; i++) id = (id << 2) | (s1[p + i] & 3u);
-                atomicOr(&bm[id >> 5], 1u << (id & 31));
-                uint32_t slot = ks_hash(id);
-                while (atomicCAS(&ht[slot], KS_EMPTY, id << 16 | (uint32_t)p) != KS_EMPTY) slot = (slot + 1) & (KS_HASH - 1);
+            for (int i = 0; i < 8; i++) id = (id << 2) | (s1[p + i] & 3u);
+            atomicOr(&bm[id >> 5], 1u << (id & 31));
+            uint32_t slot = ks_hash(id);
+            while (atomicCAS(&ht[slot], KS_EMPTY, id << 16 | (uint32_t)p) != KS_EMPTY) slot = (slot + 1) & (KS_HASH - 1);
+        }
+        __syncthreads();
+        const int t0 = (int)(ch - chunk_off[job]) * KS_CHUNK;
+        const int t1 = min(t0 + KS_CHUNK, (ngk + KS_TILE - 1) / KS_TILE);
+        const uint32_t my_cap = cap[job];
+        uint32_t *my_recs = recs + rec_off[job];
+        // the three words of the next tile are in flight while the current one is matched
+        auto fetch = [&](int tt, uint32_t &a0, uint32_t &a1, uint32_t &a2) {
+            const int gf = tt * KS_TILE + tid * KS_PPT;
+            if (tt < t1 && gf < ngk) {
+                const uint32_t *w = ix.ref2 + ((J.gpos + gf) >> 4);
+                a0 = __ldg(w); a1 = __ldg(w + 1); a2 = __ldg(w + 2);
             }
-            __syncthreads();
-            const int64_t t_end = min(t1, tile_off[job + 1]);
-            const uint32_t my_cap = cap[job];
-            uint32_t *my_recs = recs + rec_off[job];
-            for (; t < t_end; t++) {
-                const int g_first = (int)(t - tile_off[job]) * KS_TILE + tid * KS_PPT;
-                if (g_first >= ngk) continue;
-                const int64_t q0 = J.gpos + g_first;
-                const uint32_t *w = ix.ref2 + (q0 >> 4);
-                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-                const uint64_t x01 = (uint64_t)w0 << 32 | w1, x12 = (uint64_t)w1 << 32 | w2;
-                const int o0 = (int)(q0 & 15);
+        };
+        uint32_t w0 = 0, w1 = 0, w2 = 0, n0 = 0, n1 = 0, n2 = 0;
+        fetch(t0, w0, w1, w2);
+        for (int t = t0; t < t1; t++) {
+            fetch(t + 1, n0, n1, n2);
+            const int g_first = t * KS_TILE + tid * KS_PPT;
+            if (g_first < ngk) {
+                // align the 96-bit window to the thread's first position once; the 16 8-mers then sit at fixed offsets
+                const int sh = 2 * (int)((J.gpos + g_first) & 15);
+                const uint32_t X0 = __funnelshift_l(w1, w0, sh), X1 = __funnelshift_l(w2, w1, sh);
+                const int left = ngk - g_first;                      // positions of this thread that are inside the window
 #pragma unroll
                 for (int i = 0; i < KS_PPT; i++) {
-                    const int off = o0 + i;
-                    const uint64_t x = off < 16 ? x01 : x12;
-                    const uint32_t id = (uint32_t)(x >> (48 - 2 * (off & 15))) & 0xFFFFu;
-                    if (g_first + i < ngk && ((bm[id >> 5] >> (id & 31)) & 1u)) {
+                    const uint32_t id = (i <= 8 ? X0 >> (16 - 2 * i) : __funnelshift_l(X1, X0, 2 * i) >> 16) & 0xFFFFu;
+                    if (((bm[id >> 5] >> (id & 31)) & 1u) && i < left) {
                         uint32_t slot = ks_hash(id), e;
                         while ((e = ht[slot]) != KS_EMPTY) {
                             if ((e >> 16) == id) {
@@ -321,6 +324,7 @@ k_kmer_scan(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__
                     }
                 }
             }
+            w0 = n0; w1 = n1; w2 = n2;
         }
     }
 }

@@ -15,6 +15,8 @@
 // by shuffle from lane l-1, the genome base is handed down the lanes systolically.  Integer pipes only:
 // ~20 integer ops + 4 shuffles per cell-step.  Two traceback bits per cell: in registers for single-strip jobs
 // (m <= 32, n <= 64 — walked back with shuffles), in global scratch for larger ones (lane 0 walks them back).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "dartgpu_internal.h"
 
 namespace dartgpu {
@@ -29,16 +31,23 @@ __device__ __forceinline__ int ref_base(const DevIndex &ix, int64_t p)
     return (int)((__ldg(ix.ref2 + (p >> 4)) >> (30 - 2 * (int)(p & 15))) & 3);
 }
 
+__device__ __forceinline__ bool nw_thread_class(int m, int n);
+
 __global__ void __launch_bounds__(NW_THREADS)
-k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, int n_jobs,
+k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, const uint32_t *__restrict__ order,
+     const uint32_t *__restrict__ sorted_keys, int n_jobs,
      uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     int32_t *rb = rowbuf + (size_t)warp * rowbuf_per_warp;
+    // the jobs k_nw_thread does not take are the tail of the shape-sorted list (key 0xFFFF)
+    int first = 0;
+    { int lo = 0, hi = n_jobs; while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted_keys[mid] < 0xFFFFu) lo = mid + 1; else hi = mid; } first = lo; }
 
-    for (int job = warp; job < n_jobs; job += nwarps) {
+    for (int k = first + warp; k < n_jobs; k += nwarps) {
+        const int job = (int)order[k];
         const NwJobDev J = jobs[job];
         const int m = J.m, n = J.n;
         if (m <= 32 && n <= 64) {
@@ -161,15 +170,108 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
     }
 }
 
+// Jobs up to 64 x 64 cells — the bulk of every config: a mismatch or a short indel between two seeds, a gap of a few
+// dozen bases against its flank — are aligned by ONE THREAD each, 32 independent alignments per warp: row-wise sweep, the
+// previous row (S, T as int16: scores stay within +-2000 half-units, "minus infinity" is -30000) in shared memory laid out
+// [column][thread] (conflict-free), the genome bases of the job in two 64-bit registers, the 2-bit traceback flags of
+// a row written as ceil(n/16) words to the job's slice of the global flag scratch and walked back by the same thread.
+// Round-1 ncu of the warp-per-job kernel: issue-bound (66 %), 21 of 32 lanes active, ~130 thread-instructions per cell
+// (pipeline fill/drain of a 32-lane anti-diagonal sweep over a 10..1300-cell matrix, 4 shuffles per step, warp-uniform
+// traceback); a thread needs ~25 per cell.  Jobs are sorted by (n, m) first so that the alignments of a warp have the
+// same shape.
+constexpr int NWT_THREADS = 128, NWT_MAX = 64;
+constexpr int NWT_NEG = -30000;
+__device__ __forceinline__ bool nw_thread_class(int m, int n) { return m >= 1 && n >= 1 && m <= NWT_MAX && n <= NWT_MAX; }
+
+__global__ void k_nw_sort_keys(const NwJobDev *__restrict__ jobs, int n_jobs, uint32_t *keys, uint32_t *vals)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
+        const int m = jobs[j].m, n = jobs[j].n;
+        keys[j] = nw_thread_class(m, n) ? (uint32_t)(n << 7 | m) : 0xFFFFu;
+        vals[j] = (uint32_t)j;
+    }
+}
+
+__global__ void __launch_bounds__(NWT_THREADS)
+k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, const uint32_t *__restrict__ order,
+            const uint32_t *__restrict__ sorted_keys, int n_jobs, uint32_t *flags, uint8_t *ops, int32_t *nops)
+{
+    __shared__ int16_t sS[NWT_MAX + 1][NWT_THREADS], sT[NWT_MAX + 1][NWT_THREADS];
+    const int tid = threadIdx.x;
+    for (int k0 = blockIdx.x * NWT_THREADS; k0 < n_jobs; k0 += gridDim.x * NWT_THREADS) {
+        const int k = k0 + tid;
+        if (k >= n_jobs || sorted_keys[k] == 0xFFFFu) continue;       // sorted: warp-class jobs are at the end
+        const int job = (int)order[k];
+        const NwJobDev J = jobs[job];
+        const int m = J.m, n = J.n;
+        // genome bases of the job: base j-1 at bits 2(j-1) of g0 (j <= 32) / g1
+        uint64_t g0 = 0, g1 = 0;
+        for (int j = 0; j < n; j++) {
+            const uint64_t b = (uint64_t)ref_base(ix, J.gpos + j);
+            if (j < 32) g0 |= b << (2 * j); else g1 |= b << (2 * (j - 32));
+        }
+        for (int j = 0; j <= n; j++) { sS[j][tid] = (int16_t)(j == 0 ? 0 : -2 - j); sT[j][tid] = (int16_t)NWT_NEG; }
+        const int wpr = (n + 15) >> 4;
+        uint32_t *fl = flags + J.flag_off;
+        const uint8_t *s1 = codes + J.s1_off;
+        for (int i = 1; i <= m; i++) {
+            int a = (int)s1[i - 1];
+            a = (a & 4) ? 7 : (a & 3);
+            int Sl = -2 - i, Rl = NWT_NEG, Sd = sS[0][tid];
+            sS[0][tid] = (int16_t)Sl;
+            uint32_t fw = 0;
+            for (int j = 1; j <= n; j++) {
+                const int Su = sS[j][tid], Tu = sT[j][tid];
+                const int b = (int)(((j <= 32 ? g0 >> (2 * (j - 1)) : g1 >> (2 * (j - 33)))) & 3);
+                const int R = max(Rl - 1, Sl - 3);
+                const int T = max(Tu - 1, Su - 3);
+                const int h = max(Sd + (a == b ? 3 : -3), max(R, T));
+                const int S = (h / 2) * 2;
+                fw |= ((S == R ? 1u : 0u) | (S == T ? 2u : 0u)) << (((j - 1) & 15) * 2);
+                if (((j - 1) & 15) == 15 || j == n) { fl[(size_t)(i - 1) * wpr + ((j - 1) >> 4)] = fw; fw = 0; }
+                Sd = Su; Sl = S; Rl = R;
+                sS[j][tid] = (int16_t)S; sT[j][tid] = (int16_t)T;
+            }
+        }
+        int ti = m, tj = n, cnt = 0;
+        int64_t pos = J.op_off + m + n;
+        while (ti > 0 || tj > 0) {
+            int op;
+            if (ti == 0) op = 1;
+            else if (tj == 0) op = 2;
+            else {
+                const uint32_t f = (fl[(size_t)(ti - 1) * wpr + ((tj - 1) >> 4)] >> (((tj - 1) & 15) * 2)) & 3u;
+                op = (f & 1u) ? 1 : ((f & 2u) ? 2 : 0);
+            }
+            ops[--pos] = (uint8_t)op;
+            cnt++;
+            if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
+        }
+        nops[job] = cnt;
+    }
+}
+
 int nw_grid_warps() { return 148 * 8 * (NW_THREADS / 32); }
 
 void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,
-               uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, cudaStream_t st)
+               uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, NwScratch &S, cudaStream_t st)
 {
     if (n_jobs <= 0) return;
+    // thread-per-job class, sorted by shape
+    S.keys.reserve(n_jobs); S.vals.reserve(n_jobs); S.keys2.reserve(n_jobs); S.vals2.reserve(n_jobs);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, S.keys.p, S.keys2.p, S.vals.p, S.vals2.p, n_jobs, 0, 16, st);
+    S.tmp.reserve(tmp + 256);
+    int g0 = (n_jobs + 255) / 256; if (g0 > 148 * 8) g0 = 148 * 8;
+    k_nw_sort_keys<<<g0, 256, 0, st>>>(jobs, n_jobs, S.keys.p, S.vals.p);
+    tmp = S.tmp.cap;
+    cub::DeviceRadixSort::SortPairs(S.tmp.p, tmp, S.keys.p, S.keys2.p, S.vals.p, S.vals2.p, n_jobs, 0, 16, st);
+    int gt = (n_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > 148 * 6) gt = 148 * 6;
+    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, jobs, S.vals2.p, S.keys2.p, n_jobs, flags, ops, nops);
+    // everything larger: a warp per job
     int want = (n_jobs + (NW_THREADS / 32) - 1) / (NW_THREADS / 32);
     int grid = want < 148 * 8 ? want : 148 * 8;
-    k_nw<<<grid, NW_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, flags, rowbuf, rowbuf_per_warp, ops, nops);
+    k_nw<<<grid, NW_THREADS, 0, st>>>(ix, codes, jobs, S.vals2.p, S.keys2.p, n_jobs, flags, rowbuf, rowbuf_per_warp, ops, nops);
 }
 
 } // namespace dartgpu

@@ -70,10 +70,14 @@ __global__ void k_set_sv_off(int64_t ncand, CandState *cs, const int64_t *off)
 
 // One thread per candidate.  The candidate's record is worked on in registers and its seeds, when few (the normal
 // case: 1-4 seeds), in a shared-memory slot; larger candidates work in place on their HBM slice.
-constexpr int STAGE_SEEDS = 5;
+// Occupancy per phase (round-1 launch lists): the phases are latency-bound chains of dependent loads, so A, B and D run
+// 8 CTAs per SM (64 registers, 5 staged seeds); C — which extends seeds and keeps more state live — spills and slows down
+// 2x under that cap and keeps 5 CTAs per SM with 8 staged seeds.
+template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 2 ? 8 : 5, MIN_CTAS = WHICH == 2 ? 5 : 8; };
 template <int WHICH>
-__global__ void __launch_bounds__(TPB, 8) k_phase(Env E, int64_t ncand)
+__global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E, int64_t ncand)
 {
+    constexpr int STAGE_SEEDS = PhaseCfg<WHICH>::STAGE;
     __shared__ RSeed s_slot[TPB * STAGE_SEEDS];
     for (int64_t cid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cid < ncand; cid += (int64_t)gridDim.x * blockDim.x) {
         CandState c = E.cs[cid];
@@ -291,12 +295,12 @@ static void nw_round(dartgpu_ctx *c, DevicePipe *D, NwJobDev *jobs, int nj, bool
     size_t rb = multi ? (size_t)2 * (max_n + 1) : 0;
     D->rowbuf.reserve(rb * nw_grid_warps() + 1);
     DG_CUDA(cudaEventRecord(c->ev[10], st));
-    launch_nw(c->ix, c->d_codes.p, jobs, nj, D->flags.p, D->rowbuf.p, rb, ops.p, nops.p, st);
+    launch_nw(c->ix, c->d_codes.p, jobs, nj, D->flags.p, D->rowbuf.p, rb, ops.p, nops.p, c->nwscratch, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[11], st));
     DG_CUDA(cudaStreamSynchronize(st));
     add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
-    c->stats.kernel_launches += 6;
+    c->stats.kernel_launches += 4 + NW_LAUNCHES;
     c->stats.nw_jobs += nj;
 }
 
@@ -339,7 +343,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     D->kjobs.reserve(pool_total / 12 + 2); D->khits.reserve(pool_total / 12 + 2);
     D->jobsB.reserve(pool_total / 3 + 4); D->jobsC.reserve(pool_total + 4);
     DG_CUDA(cudaMemsetAsync(D->counters.p, 0, 8 * sizeof(int32_t), st));
-    c->stats.kernel_launches += 8;
+    c->stats.kernel_launches += 4 + NW_LAUNCHES;
 
     Env E{};
     E.P = PhaseParams{P.max_gaps, P.max_intron, P.min_intron, P.max_mismatch, P.multi_hit, P.pair_end, P.all_sj};

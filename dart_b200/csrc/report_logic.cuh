@@ -75,6 +75,38 @@ struct RefView {
         int64_t q = 2 * G - 1 - p;
         return 3 - ((pac[q >> 2] >> ((~q & 3) << 1)) & 3);
     }
+    // 32 bases starting at p as one u64, base k at bits 62-2k; positions outside [0,2G) read as 0 like code().
+    // Round-1 ncu (k_phase<2>, full-size config[2]): a third of the phase's instructions and most of its stalls were
+    // single-base code() calls — a dependent load plus two range checks per base.
+    HD uint64_t window32(int64_t p) const
+    {
+        if (ref2 && p >= 0 && p + 32 <= 2 * G) {         // the device table has guard words behind 2G
+            const uint32_t *w = ref2 + (p >> 4);
+            const int sh = 2 * (int)(p & 15);
+            const uint64_t hi = (uint64_t)w[0] << 32 | w[1];
+            return sh ? (hi << sh) | ((uint64_t)w[2] >> (32 - sh)) : hi;
+        }
+        uint64_t x = 0;
+        for (int k = 0; k < 32; k++) x |= (uint64_t)code(p + k) << (62 - 2 * k);
+        return x;
+    }
+};
+
+// bases [at, at+n) of a window32 value, right-aligned (n <= 31)
+HD uint64_t win_bases(uint64_t w, int at, int n) { return n <= 0 ? 0 : (w << (2 * at)) >> (64 - 2 * n); }
+
+// Sequential reader: keeps the 16-base word under the cursor in a register (gapped_partition, simple_enough, the
+// CIGAR builders walk the genome base by base).
+struct RefCursor {
+    const RefView &rv; int64_t wi; uint32_t w;
+    HD explicit RefCursor(const RefView &r) : rv(r), wi(-1), w(0) {}
+    HD int code(int64_t p)
+    {
+        if (!rv.ref2 || p < 0 || p >= 2 * rv.G) return rv.code(p);
+        const int64_t i = p >> 4;
+        if (i != wi) { wi = i; w = rv.ref2[i]; }
+        return (int)((w >> (30 - 2 * (int)(p & 15))) & 3);
+    }
 };
 
 // read codes: 0..3 = ACGT, 8..11 = acgt, 4 = other, 5 = 'N'.  The reference compares raw characters against the
@@ -353,12 +385,13 @@ HDN void gapped_partition(const Env &E, const uint8_t *gap, int rGaps, const RSe
     while (last1 >= 0 && A1.ops[last1] == 2) last1--;          // a2[t] == '-'  <=> op 2
     {
         int i = 0, p = 0, s = 0; int64_t g = g1, fill = L.gPos + L.gLen + rGaps;
+        RefCursor ref(E.ref), reff(E.ref);
         for (int t = 0; t < A1.k; t++) {
             int op = A1.ops[t];
             bool rgap = op == 1;                                 // '-' in the read string
             int gc = -1;
-            if (op != 2) gc = E.ref.code(g++);
-            else if (t > last1) gc = E.ref.code(fill++);
+            if (op != 2) gc = ref.code(g++);
+            else if (t > last1) gc = reff.code(fill++);
             if (!rgap && gc >= 0 && raw_eq(gap[i], gc)) s++;
             if (!rgap) { p++; i++; }
             Rv[p] = s;
@@ -372,14 +405,15 @@ HDN void gapped_partition(const Env &E, const uint8_t *gap, int rGaps, const RSe
         int ri = 0; int64_t gj = g2;
         for (int t = 0; t < A2.k; t++) { if (A2.ops[t] != 1) ri++; if (A2.ops[t] != 2) gj++; }
         int p = 0, s = 0;
+        RefCursor ref(E.ref), reff(E.ref);
         for (int t = A2.k - 1; t >= 0; t--) {
             int op = A2.ops[t];
             bool rgap = op == 1;
             if (op != 2) gj--;
             if (!rgap) ri--;
             int gc = -1;
-            if (op != 2) gc = E.ref.code(gj);
-            else if (t < first2) gc = E.ref.code(g2 - (first2 - 1 - t));   // a4[i] for i = first2-1 .. 0 gets ref[g2], ref[g2-1], ..
+            if (op != 2) gc = ref.code(gj);
+            else if (t < first2) gc = reff.code(g2 - (first2 - 1 - t));   // a4[i] for i = first2-1 .. 0 gets ref[g2], ref[g2-1], ..
             if (!rgap && gc >= 0 && raw_eq(gap[ri], gc)) s++;
             if (!rgap) p++;
             Lv[rGaps - p] = s;
@@ -395,35 +429,37 @@ HDN void gapped_partition(const Env &E, const uint8_t *gap, int rGaps, const RSe
     P_out = P;
 }
 
-HD bool same_fragment(const Env &E, int64_t L, int64_t R, int shift)
+// motifs GT/AG, CT/AC, GC/AG, CT/GC as codes (main.cpp:18), donor pair << 4 | acceptor pair
+HD int motif_pairs(int type)
 {
-    if (shift > 0) { for (int i = 0; i < shift; i++, L++, R++) if (E.ref.code(L) != E.ref.code(R)) return false; }
-    else { shift = -shift; L -= shift; R -= shift; for (int i = 0; i < shift; i++, L++, R++) if (E.ref.code(L) != E.ref.code(R)) return false; }
-    return true;
-}
-
-// motifs GT/AG, CT/AC, GC/AG, CT/GC as codes (main.cpp:18)
-HD int motif_code(int type, int k)
-{
-    const int m[4][4] = {{2, 3, 0, 2}, {1, 3, 0, 1}, {2, 1, 0, 2}, {1, 3, 2, 1}};
-    return m[type][k];
+    const int m[4] = {(2 << 2 | 3) << 4 | (0 << 2 | 2), (1 << 2 | 3) << 4 | (0 << 2 | 1), (2 << 2 | 1) << 4 | (0 << 2 | 2), (1 << 2 | 3) << 4 | (2 << 2 | 1)};
+    return m[type];
 }
 HD int shift_of(int i) { return i == 0 ? 0 : ((i & 1) ? (i + 1) / 2 : -(i / 2)); }   // 0,1,-1,2,-2,..,9,-9
 
-HDN int find_junction(const Env &E, int type, const RSeed &l, const RSeed &r)
+// IdentifySpliceJunction (AlignmentCandidates.cpp:732-756) + CheckSeqFragment (:702-730).  All bases it can look at lie in
+// ref[L-9, L+11) and ref[R-11, R+9): two 32-base windows are loaded once and every comparison is a register operation.
+struct JunctionWindows { uint64_t WL, WR; };    // WL starts at L-9, WR at R-11
+HD JunctionWindows junction_windows(const Env &E, const RSeed &l, const RSeed &r)
+{
+    JunctionWindows w; w.WL = E.ref.window32(l.gPos + l.gLen - 9); w.WR = E.ref.window32(r.gPos - 11);
+    return w;
+}
+HDN int find_junction(const JunctionWindows &W, int type, const RSeed &l, const RSeed &r)
 {
     int i = l.rLen < r.rLen ? l.rLen : r.rLen, j = l.gLen < r.gLen ? l.gLen : r.gLen;
     if (i < j) j = i;
     if (j > 9) j = 9;
     j <<= 1;
-    int64_t L = l.gPos + l.gLen, R = r.gPos;
+    const int mp = motif_pairs(type);
     int shift = 0;
     for (i = 0; i <= j; i++) {
         shift = shift_of(i);
-        if (shift != 0 && !same_fragment(E, L, R, shift)) continue;
-        int64_t g1 = L + shift, g2 = R - 2 + shift;
-        if (E.ref.code(g1) == motif_code(type, 0) && E.ref.code(g1 + 1) == motif_code(type, 1) &&
-            E.ref.code(g2) == motif_code(type, 2) && E.ref.code(g2 + 1) == motif_code(type, 3)) break;
+        // same_fragment: ref[L, L+shift) == ref[R, R+shift)  (shift > 0)  or  ref[L+shift, L) == ref[R+shift, R)  (shift < 0)
+        if (shift > 0 && win_bases(W.WL, 9, shift) != win_bases(W.WR, 11, shift)) continue;
+        if (shift < 0 && win_bases(W.WL, 9 + shift, -shift) != win_bases(W.WR, 11 + shift, -shift)) continue;
+        // donor pair at L+shift, acceptor pair at R-2+shift
+        if ((int)win_bases(W.WL, 9 + shift, 2) == (mp >> 4) && (int)win_bases(W.WR, 9 + shift, 2) == (mp & 15)) break;
     }
     return i > j ? 10 : shift;
 }
@@ -437,7 +473,7 @@ HDN int check_splice_junction(const Env &E, RSeed *sv, int n)
         int mis = 0, cost = 0, found = 0;
         for (int i = 1; i < n; i++) {
             if ((sv[i].PosDiff - sv[i - 1].PosDiff) > E.P.min_intron && sv[i - 1].simple && sv[i].simple) {
-                int shift = find_junction(E, type, sv[i - 1], sv[i]);
+                int shift = find_junction(junction_windows(E, sv[i - 1], sv[i]), type, sv[i - 1], sv[i]);
                 if (shift != 10) found++; else mis++;
                 cost += shift < 0 ? -shift : shift;
             }
@@ -451,7 +487,7 @@ HDN int check_splice_junction(const Env &E, RSeed *sv, int n)
         int32_t cnt = 0;
         for (int i = 1; i < n; i++) sv[i].job = 10;
         for (int i = 1; i < n; i++)
-            if ((sv[i].PosDiff - sv[i - 1].PosDiff) > E.P.min_intron && sv[i - 1].simple && sv[i].simple) { sv[i].job = find_junction(E, best_type, sv[i - 1], sv[i]); cnt++; }
+            if ((sv[i].PosDiff - sv[i - 1].PosDiff) > E.P.min_intron && sv[i - 1].simple && sv[i].simple) { sv[i].job = find_junction(junction_windows(E, sv[i - 1], sv[i]), best_type, sv[i - 1], sv[i]); cnt++; }
         for (int j = 1; j < n; j++) {
             int shift = sv[j].job;
             if (shift != 10) {
@@ -541,7 +577,8 @@ HD bool simple_enough(const Env &E, const uint8_t *rc, const RSeed &sp, int *n_o
 {
     if (sp.rLen != sp.gLen) return false;
     int nm = 0;
-    for (int i = 0; i < sp.rLen; i++) if (!raw_eq(rc[sp.rPos + i], E.ref.code(sp.gPos + i))) nm++;
+    RefCursor ref(E.ref);
+    for (int i = 0; i < sp.rLen; i++) if (!raw_eq(rc[sp.rPos + i], ref.code(sp.gPos + i))) nm++;
     *n_out = nm;
     return nm <= 2 && nm <= (int)(sp.rLen * 0.2);
 }
@@ -614,12 +651,13 @@ HDN int add_cigar(const Env &E, const uint8_t *s1, int64_t gpos, const Aln &A, i
 {
     char state = '*';
     int c = 0, score = 0;
+    RefCursor ref(E.ref);
     for (int t = t0; t < t1; t++) {
         int op = A.ops[t];
         char want;
         if (op == 1) { want = 'D'; g++; }
         else if (op == 2) { want = 'I'; i++; }
-        else { want = 'M'; if (raw_eq(s1[i], E.ref.code(g))) score++; i++; g++; }
+        else { want = 'M'; if (raw_eq(s1[i], ref.code(g))) score++; i++; g++; }
         if (state == want) c++;
         else { if (c > 0) cv.push(c, state); c = 1; state = want; }
     }
@@ -632,11 +670,12 @@ HDN bool local_quality_ok(const Env &E, const uint8_t *s1, int64_t gpos, const A
 {
     int type = -1, nn = 0, mis = 0, status = 0, i = 0;
     int64_t g = gpos;
+    RefCursor ref(E.ref);
     for (int t = 0; t < A.k; t++) {
         int op = A.ops[t], ty;
         if (op == 1) { ty = 0; g++; }
         else if (op == 2) { ty = 1; i++; }
-        else { ty = 2; nn++; if (!raw_eq(s1[i], E.ref.code(g))) mis++; i++; g++; }
+        else { ty = 2; nn++; if (!raw_eq(s1[i], ref.code(g))) mis++; i++; g++; }
         if (type != ty) { type = ty; status++; }
     }
     return !(status >= 4 || (mis >= 3 && mis >= (int)(nn * 0.3)));

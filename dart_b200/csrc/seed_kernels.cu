@@ -98,20 +98,40 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     const int K = ix.ktab ? ix.ktab_k : 0;
     const uint32_t kmask2 = K >= 16 ? ~0u : (1u << (2 * K)) - 1u, kmask1 = (1u << K) - 1u;
 
-    bool own = true, have_read = false, searching = false;
+    bool own = true, have_read = false, searching = false, finished = false, ended = false;
     int r = 0, rl = 0, start = 0, p = 0, cw = -1;
     int64_t wbase = 0;
     uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0;
     IdxT x1 = 0;
     uint32_t st_steps = 0, st_splits = 0;
 
+    // Two kinds of work alternate in a lane: rank steps (the hot path) and, every ~20 steps, the "turn-around" — record
+    // the finished segment, find the next search start or the next read, gather the K-mer start.  ncu of the first
+    // thread-per-chain version: 14 of 32 lanes active on average, because at almost every iteration SOME lane was in its
+    // turn-around and the warp executed both paths.  Lanes now wait for company: the turn-around runs only when at least
+    // TURN_BATCH lanes need it (or nobody is stepping), so its ~100 instructions are shared by several lanes.
+    constexpr int TURN_BATCH = 6;
     for (;;) {
-        if (!searching) {
-            bool done = false;
+        const unsigned need_m = __ballot_sync(FULL, !searching && !finished);
+        const unsigned step_m = __ballot_sync(FULL, searching);
+        if ((need_m | step_m) == 0) break;
+        if (!searching && !finished && (__popc(need_m) >= TURN_BATCH || step_m == 0)) {
+            if (ended) {                                  // the segment that just ended: bwt_search.cpp:173, IdentifySeedPairs' advance
+                const int len = p - start;
+                if (x2 <= a.max_dup && len >= 16) {
+                    if ((int)nr < a.cap_rec) {
+                        SearchRec rec; rec.sa_begin = x1; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
+                        a.recs[(int64_t)r * a.cap_rec + nr] = rec;
+                    }
+                    nr++; nh += x2;
+                    start += len;
+                } else start++;
+                ended = false;
+            }
             for (;;) {
                 if (!have_read) {
                     if (own) { r = atomicAdd(&s_next, 1); if (r >= r_end) own = false; }
-                    if (!own) { r = a.steal_base + (int)atomicAdd(a.steal, 1u); if (r >= a.n_reads) { done = true; break; } }
+                    if (!own) { r = a.steal_base + (int)atomicAdd(a.steal, 1u); if (r >= a.n_reads) { finished = true; break; } }
                     rl = a.rlen[r];
                     wbase = a.dev_off[r] >> 4;
                     start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
@@ -125,67 +145,59 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                 a.nrec[r] = nr; a.nhits[r] = nh;
                 have_read = false;
             }
-            if (done) break;
-            // the first K bases of the search in one gather (KmerStart), when they are all inside the read, unambiguous
-            // and the K-mer occurs; otherwise start from the single base as the reference does
-            bool jumped = false;
-            if (K > 0 && start + K <= rl) {
-                const int sh = start & 15;
-                uint32_t bits = wcode >> (2 * sh), ambs = wamb >> sh;
-                if (sh + K > 16) {
-                    const uint2 w2 = __ldg(a.packed + wbase + cw + 1);
-                    bits |= sh ? w2.x << (32 - 2 * sh) : 0u; ambs |= w2.y << (16 - sh);
-                }
-                if ((ambs & kmask1) == 0) {
-                    const KmerStart e = ix.ktab[bits & kmask2];
-                    if (e.x2 != 0) {
-                        x1 = (IdxT)e.x1; x2 = e.x2; p = start + K;
-                        st_steps += K - 1; st_splits += e.splits;
-                        jumped = true;
+            if (!finished) {
+                // the first K bases of the search in one gather (KmerStart), when they are all inside the read, unambiguous
+                // and the K-mer occurs; otherwise start from the single base as the reference does
+                bool jumped = false;
+                if (K > 0 && start + K <= rl) {
+                    const int sh = start & 15;
+                    uint32_t bits = wcode >> (2 * sh), ambs = wamb >> sh;
+                    if (sh + K > 16) {
+                        const uint2 w2 = __ldg(a.packed + wbase + cw + 1);
+                        bits |= sh ? w2.x << (32 - 2 * sh) : 0u; ambs |= w2.y << (16 - sh);
+                    }
+                    if ((ambs & kmask1) == 0) {
+                        const KmerStart e = ix.ktab[bits & kmask2];
+                        if (e.x2 != 0) {
+                            x1 = (IdxT)e.x1; x2 = e.x2; p = start + K;
+                            st_steps += K - 1; st_splits += e.splits;
+                            jumped = true;
+                        }
                     }
                 }
-            }
-            if (!jumped) {
-                const int c0 = (wcode >> ((start & 15) * 2)) & 3;
-                x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
-                p = start + 1;
-            }
-            searching = true;
-        }
-        bool end = p >= rl;
-        if (!end) {
-            if ((p >> 4) != cw) { cw = p >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
-            end = (wamb >> (p & 15)) & 1u;
-        }
-        if (!end) {
-            const IdxT k = x1 - 1, l = k + x2;
-            const IdxT kk = k - (k >= primary), ll = l - (l >= primary);
-            const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3u);     // complement: backward step of revcomp(P)
-            const uint64_t bk = (uint64_t)kk >> 6, bl = (uint64_t)ll >> 6;
-            const OccBlock Bk = load_block(occ, bk);
-            OccBlock Bl = Bk;
-            if (bl != bk) Bl = load_block(occ, bl);                      // narrow intervals sit in one block: one load
-            const uint32_t ok = block_rank(Bk, (uint32_t)kk & 63u, c), ol = block_rank(Bl, (uint32_t)ll & 63u, c);
-            st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
-            const uint32_t n2 = ol - ok;
-            if (n2 == 0) end = true;
-            else {
-                x1 = (IdxT)s_L2[c] + 1 + ok;
-                x2 = n2;
-                p++;
-            }
-        }
-        if (end) {
-            const int len = p - start;
-            if (x2 <= a.max_dup && len >= 16) { // bwt_search.cpp:173
-                if ((int)nr < a.cap_rec) {
-                    SearchRec rec; rec.sa_begin = x1; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
-                    a.recs[(int64_t)r * a.cap_rec + nr] = rec;
+                if (!jumped) {
+                    const int c0 = (wcode >> ((start & 15) * 2)) & 3;
+                    x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
+                    p = start + 1;
                 }
-                nr++; nh += x2;
-                start += len;
-            } else start++;
-            searching = false;
+                searching = true;
+            }
+        }
+        if (searching) {
+            bool end = p >= rl;
+            if (!end) {
+                if ((p >> 4) != cw) { cw = p >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+                end = (wamb >> (p & 15)) & 1u;
+            }
+            if (!end) {
+                const IdxT k = x1 - 1, l = k + x2;
+                const IdxT kk = k - (k >= primary), ll = l - (l >= primary);
+                const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3u);     // complement: backward step of revcomp(P)
+                const uint64_t bk = (uint64_t)kk >> 6, bl = (uint64_t)ll >> 6;
+                const OccBlock Bk = load_block(occ, bk);
+                OccBlock Bl = Bk;
+                if (bl != bk) Bl = load_block(occ, bl);                      // narrow intervals sit in one block: one load
+                const uint32_t ok = block_rank(Bk, (uint32_t)kk & 63u, c), ol = block_rank(Bl, (uint32_t)ll & 63u, c);
+                st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
+                const uint32_t n2 = ol - ok;
+                if (n2 == 0) end = true;
+                else {
+                    x1 = (IdxT)s_L2[c] + 1 + ok;
+                    x2 = n2;
+                    p++;
+                }
+            }
+            if (end) { searching = false; ended = true; }
         }
     }
     __syncwarp();

@@ -212,6 +212,11 @@ def test_nw_matches_oracle():
         gpos = rng.randint(0, 2 * G - 1200)
         s1 = _mut(rng, _win(O, gpos, m), 0.08) or b"G"
         add(s1, gpos, min(2 * len(s1), rng.randint(30, 520)))
+    for m, n in [(64, 64), (64, 65), (65, 64), (1, 64), (64, 1), (63, 33), (33, 63), (32, 32), (17, 48), (64, 17)]:   # class boundaries
+        for rate in (0.0, 0.1, 0.4):
+            gpos = rng.randint(0, 2 * G - 200)
+            s1 = (_mut(rng, _win(O, gpos, max(m, n)), rate) * 2)[:m]
+            add(s1, gpos, n)
     add(b"ACGTN", 1000, 5); add(b"N", 5000, 1); add(b"", 7000, 4); add(b"ACG", 9000, 0); add(b"", 100, 0)
     got = M.nw_alignment(bytes(frags), jobs)
     assert len(got) == len(jobs)
