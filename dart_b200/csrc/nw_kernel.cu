@@ -149,22 +149,36 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
             __syncwarp();
         }
         __syncwarp();
-        if (lane == 0) {
-            int i = m, j = n, k = 0;
+        {
+            // Traceback, warp-uniform: the 32 lanes hold the flag words of 32 consecutive rows (ending at the current row) for
+            // the current 16-column word and hand them round by shuffle; one reload every >= 16 steps instead of one
+            // dependent L2 round trip per step (round-1 launch list of the 2x250 config: a 250 x 500 job spent ~3x longer
+            // walking back through global memory on lane 0 than sweeping).
+            int ti = m, tj = n, k = 0;
             int64_t pos = J.op_off + m + n;
-            while (i > 0 || j > 0) {
+            int base_i = -1, wcol = -1;
+            uint32_t myw = 0;
+            while (ti > 0 || tj > 0) {
                 int op;
-                if (i == 0) op = 1;
-                else if (j == 0) op = 2;
+                if (ti == 0) op = 1;
+                else if (tj == 0) op = 2;
                 else {
-                    uint32_t f = (__ldcg(fl + (size_t)(i - 1) * wpr + ((j - 1) >> 4)) >> (((j - 1) & 15) * 2)) & 3u;
+                    const int wc = (tj - 1) >> 4;
+                    if (wc != wcol || base_i - ti >= 32 || base_i < ti) {
+                        base_i = ti; wcol = wc;
+                        const int row = base_i - 1 - lane;
+                        myw = row >= 0 ? __ldcg(fl + (size_t)row * wpr + wcol) : 0u;
+                    }
+                    const uint32_t w = __shfl_sync(FULLM, myw, base_i - ti);
+                    const uint32_t f = (w >> (((tj - 1) & 15) * 2)) & 3u;
                     op = (f & 1u) ? 1 : ((f & 2u) ? 2 : 0);
                 }
-                ops[--pos] = (uint8_t)op;
+                --pos;
+                if (lane == 0) ops[pos] = (uint8_t)op;
                 k++;
-                if (op == 1) j--; else if (op == 2) i--; else { i--; j--; }
+                if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
             }
-            nops[job] = k;
+            if (lane == 0) nops[job] = k;
         }
         __syncwarp();
     }

@@ -70,30 +70,52 @@ __global__ void k_set_sv_off(int64_t ncand, CandState *cs, const int64_t *off)
 
 // One thread per candidate.  The candidate's record is worked on in registers and its seeds, when few (the normal
 // case: 1-4 seeds), in a shared-memory slot; larger candidates work in place on their HBM slice.
-// Occupancy per phase (round-1 launch lists): the phases are latency-bound chains of dependent loads, so A, B and D run
-// 8 CTAs per SM (64 registers, 5 staged seeds); C — which extends seeds and keeps more state live — spills and slows down
-// 2x under that cap and keeps 5 CTAs per SM with 8 staged seeds.
-template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 2 ? 8 : 5, MIN_CTAS = WHICH == 2 ? 5 : 8; };
+// A candidate that emits no job in a phase does not have to wait for that phase's batched k-mer / NW launch: it goes
+// straight on to the next phase in the same thread, up to and including C (D needs the CIGAR offsets of a scan).  On
+// BASELINE config[1] nearly every candidate is a single seed pair with nothing to repair, so A, B and C run in one pass
+// over the candidate table and the later kernels skip it on a one-byte stage marker (round-1 launch list: the four
+// phases were 1.6 ms of a 5.6 ms step, each re-reading and re-writing the 104-byte record and its seeds).
+// Occupancy: the phases are latency-bound chains of dependent loads; C keeps the most state live (96 registers), and any
+// kernel that may run it takes its configuration (5 CTAs per SM, 8 staged seeds); D alone runs 8 CTAs per SM.
+template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 3 ? 5 : 8, MIN_CTAS = WHICH == 3 ? 8 : 5; };
 template <int WHICH>
 __global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E, int64_t ncand)
 {
     constexpr int STAGE_SEEDS = PhaseCfg<WHICH>::STAGE;
     __shared__ RSeed s_slot[TPB * STAGE_SEEDS];
     for (int64_t cid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cid < ncand; cid += (int64_t)gridDim.x * blockDim.x) {
+        if (WHICH != 0 && WHICH != 3 && E.stage[cid] != WHICH) continue;    // already past this phase
         CandState c = E.cs[cid];
-        if (!c.live) { if (WHICH == 3) { E.cs[cid].AlnScore = 0; E.cs[cid].cig_n = 0; E.cs[cid].text_len = 0; } continue; }
+        if (!c.live) {
+            if (WHICH == 0) E.stage[cid] = 3;
+            if (WHICH == 3) { E.cs[cid].AlnScore = 0; E.cs[cid].cig_n = 0; E.cs[cid].text_len = 0; }
+            continue;
+        }
         RSeed *g = E.pool + c.sv_off, *sv = g;
         const bool staged = phase_seed_bound(c, WHICH) <= STAGE_SEEDS;
         if (staged) {
             sv = s_slot + threadIdx.x * STAGE_SEEDS;
             if (WHICH != 0) for (int i = 0; i < c.sv_n; i++) sv[i] = g[i];
         }
-        if (WHICH == 0) phase_a(E, c, sv);
-        else if (WHICH == 1) phase_b(E, c, sv);
-        else if (WHICH == 2) phase_c(E, c, sv);
-        else phase_d(E, c, sv);
+        int next = WHICH + 1;
+        if (WHICH == 0) {
+            phase_a(E, c, sv);
+            bool waits = false;
+            for (int i = 1; i < c.sv_n; i++) waits |= sv[i].job >= 0;
+            if (!waits && (!staged || phase_seed_bound(c, 1) <= STAGE_SEEDS)) { phase_b(E, c, sv); next = 2; }
+        }
+        if (WHICH == 1) phase_b(E, c, sv);
+        if ((WHICH == 0 && next == 2) || WHICH == 1) {
+            if (c.n_ext == 0 && (!staged || phase_seed_bound(c, 2) <= STAGE_SEEDS)) {
+                Env E2 = E; E2.njobs = E.njobs_c; E2.njob_count = E.njob_count_c;
+                phase_c(E2, c, sv); next = 3;
+            }
+        }
+        if (WHICH == 2) phase_c(E, c, sv);
+        if (WHICH == 3) phase_d(E, c, sv);
         if (staged) for (int i = 0; i < c.sv_n; i++) g[i] = sv[i];
         E.cs[cid] = c;
+        if (WHICH != 3) E.stage[cid] = (uint8_t)next;
     }
 }
 
@@ -223,6 +245,7 @@ struct DevicePipe {
     DevBuf<uint32_t> u32_a, u32_b, u32_c, text_len, njunc;
     DevBuf<CandState> cs;
     DevBuf<RSeed> pool;
+    DevBuf<uint8_t> stage;
     DevBuf<KmerJobDev> kjobs;
     DevBuf<dartgpu_kmer_hit> khits;
     DevBuf<NwJobDev> jobsB, jobsC;
@@ -352,6 +375,11 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     E.codes = c->d_codes.p; E.code_off = c->d_dev_off.p; E.rlen = c->d_rlen.p; E.keys = c->d_keys.p;
     E.cs = D->cs.p; E.pool = D->pool.p;
     E.kjobs = D->kjobs.p; E.kjob_count = D->counters.p + 0; E.khits = D->khits.p;
+    E.njobs = D->jobsB.p; E.njob_count = D->counters.p + 1;          // phase B's queue (also used by candidates fast-tracked out of A)
+    E.njobs_c = D->jobsC.p; E.njob_count_c = D->counters.p + 2;      // phase C's queue
+    D->stage.reserve(ncand + 1);
+    DG_CUDA(cudaMemsetAsync(D->stage.p, 0, (size_t)ncand + 1, st));
+    E.stage = D->stage.p;
 
     // ---- phase A -> 8-mer re-seeding ----
     k_phase<0><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);

@@ -124,7 +124,9 @@ struct Env {
     CandState *cs; RSeed *pool;
     // job queues
     KmerJobDev *kjobs; int32_t *kjob_count; const dartgpu_kmer_hit *khits;
-    NwJobDev *njobs; int32_t *njob_count;
+    NwJobDev *njobs; int32_t *njob_count;       // queue of the phase that runs (B: gap pairs, C: non-simple pairs)
+    NwJobDev *njobs_c; int32_t *njob_count_c;    // phase C's queue, for candidates that run A-B-C in one go
+    uint8_t *stage;                              // per candidate: the next phase it has to run (device kernels only)
     const uint8_t *ops; const int32_t *nops;     // NW results of the round being consumed (right-aligned per job)
     const NwJobDev *done_jobs;                   // the jobs those results belong to
     int32_t *xscratch;                           // Rvec/Lvec scratch of the gap-extension jobs

@@ -12,7 +12,12 @@ from dart_b200 import capi  # noqa: E402
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 g, idx = bench.prepare_genome()
-M = capi.Mapper(idx, device=0, pair_end=1)
+params = dict(pair_end=1)
+if bench.MIS:
+    params["max_mismatch"] = int(bench.MIS)
+if bench.WORKLOAD == "c5":
+    params.update(multi_hit=1, max_dup=10000, all_sj=1)
+M = capi.Mapper(idx, device=0, **params)
 batch = bench.as_batch(*bench.make_pairs(g, pairs, 0))
 for _ in range(iters):
     M.map_reads(batch, copy=False)
