@@ -276,8 +276,13 @@ def main():
     st = {k: sum(x[k] for x in sts) for k in sts[0]}          # work and kernel time summed over the contexts of this rank
     st_e2e = {k: sum(x[k] for x in sts_e2e) for k in sts_e2e[0]}
 
-    # kernel-only seeding over the whole batch on one context (no host orchestration, no copies): roofline of the dominant kernel
+    # one context alone on the GPU over the whole batch: per-kernel times without the other contexts' kernels in between
+    # (the per-step sums above are CUDA-event intervals on streams that share the device)
     M.upload_reads(batch)
+    M.map_reads(batch, True, False)
+    M.map_reads(batch, True, False)
+    alone = M.stats()
+    # kernel-only seeding over the whole batch on one context (no host orchestration, no copies): roofline of the dominant kernel
     M.seed_resident()
     ms_k = []
     for _ in range(max(3, args.steps)):
@@ -297,7 +302,8 @@ def main():
         traffic = None
         try:   # DRAM bytes of the ncu capture, scaled from its launch (400 k reads) to this launch
             t = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_ncu.json")))
-            traffic = int(t["dram_bytes_per_launch"] * n_reads / t["reads_in_launch"]) if WORKLOAD == "c2" else None
+            key = {"c2": "config1", "c3": "config2_fullsize"}.get(WORKLOAD if WORKLOAD == "c2" or SCALE == 1.0 else "")
+            traffic = int(t[key]["dram_bytes_per_launch"] * n_reads / t[key]["reads_in_launch"]) if key in t else None
         except Exception:
             pass
         line = {
@@ -317,7 +323,9 @@ def main():
                                  else "Occ table larger than L2: 64-byte gathers from HBM"},
             "kernels_ms_per_step": {k: st[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h", "ms_host")},
             "work_per_step": {k: int(st[k]) for k in ("ext_steps", "ext_blocks", "lf_steps", "hits", "seeds", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases")},
-            "nw_gcups": (st["nw_cells"] / (st["ms_nw"] * 1e-3) / 1e9) if st["ms_nw"] > 0 else None,
+            "kernels_ms_one_context_alone": {k: alone[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h")},
+            "nw_gcups": (alone["nw_cells"] / (alone["ms_nw"] * 1e-3) / 1e9) if alone["ms_nw"] > 0 else None,
+            "seed_gbs": achieved,
         }
         if world == 1:
             try:

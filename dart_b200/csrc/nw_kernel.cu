@@ -9,12 +9,14 @@
 //   * full matrix, no band (a band could change the traceback);
 //   * traceback priority S==R (gap in read, consumes genome), then S==T, else diagonal.
 //
-// One warp per job, many jobs in flight (jobs are small: tens to a few hundred cells on average).  The matrix
-// is swept in strips of 32 rows; inside a strip the warp advances along anti-diagonals: lane l owns row l of
-// the strip and at step t computes column t-l.  Left neighbours stay in registers, upper neighbours arrive
-// by shuffle from lane l-1, the genome base is handed down the lanes systolically.  Integer pipes only:
-// ~20 integer ops + 4 shuffles per cell-step.  Two traceback bits per cell: in registers for single-strip jobs
-// (m <= 32, n <= 64 — walked back with shuffles), in global scratch for larger ones (lane 0 walks them back).
+// Two kernels, jobs binned by shape:
+//   k_nw_thread  jobs up to 64 x 64 (the bulk of every config): ONE THREAD per alignment, see below;
+//   k_nw         everything larger: one warp per job.  The matrix is swept in strips of 128 rows; lane l owns 4 consecutive
+//                rows and at step t computes column t-l+1 of all four (anti-diagonal wavefront over the lanes).  Left
+//                neighbours stay in registers, the row above a lane's first row arrives by shuffle from lane l-1, the genome
+//                base is handed down the lanes systolically: 3 shuffles per 4 cells.  Two traceback bits per cell go to
+//                global scratch, 16 cells per word, and are walked back by the whole warp (32 rows of flag words in
+//                registers, handed round by shuffle).  Integer pipes only.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "dartgpu_internal.h"
@@ -24,6 +26,7 @@ namespace dartgpu {
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr int NW_THREADS = 128;
 constexpr int NW_NEG = -131072;
+constexpr int NW_ROWS = 4;                 // rows per lane in the warp-per-job kernel: strips of 128 rows
 
 __device__ __forceinline__ int ref_base(const DevIndex &ix, int64_t p)
 {
@@ -50,72 +53,33 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
         const int job = (int)order[k];
         const NwJobDev J = jobs[job];
         const int m = J.m, n = J.n;
-        if (m <= 32 && n <= 64) {
-            // ---- small job (the overwhelming majority: a mismatch or a short indel between two seeds): one strip, the
-            // traceback bits stay in registers (2 x 64 bits per row) and are walked back with shuffles — no global
-            // round trips between the sweep and the traceback.
-            const int i = lane + 1;
-            const bool rowok = i <= m;
-            int a = rowok ? (int)codes[J.s1_off + lane] : 7;
-            a = (a & 4) ? 7 : (a & 3);
-            const int b0reg = lane < n ? ref_base(ix, J.gpos + lane) : 0;
-            const int b1reg = lane + 32 < n ? ref_base(ix, J.gpos + lane + 32) : 0;
-            int Sl = -2 - i, Rl = NW_NEG, Sd = (i == 1) ? 0 : -2 - (i - 1);
-            int So = 0, To = 0, bo = 0;
-            uint64_t flo = 0, fhi = 0;
-            const int steps = n + m - 1;
-            for (int t = 0; t < steps; t++) {
-                int Su = __shfl_up_sync(FULLM, So, 1);
-                int Tu = __shfl_up_sync(FULLM, To, 1);
-                int b = __shfl_up_sync(FULLM, bo, 1);
-                const int b0 = t < 32 ? __shfl_sync(FULLM, b0reg, t) : __shfl_sync(FULLM, b1reg, t - 32);
-                const int j = t - lane + 1;
-                if (lane == 0) { Su = -2 - j; Tu = NW_NEG; b = b0; }
-                if (rowok && j >= 1 && j <= n) {
-                    int R = max(Rl - 1, Sl - 3);
-                    int T = max(Tu - 1, Su - 3);
-                    int h = max(Sd + (a == b ? 3 : -3), max(R, T));
-                    int S = (h / 2) * 2;
-                    uint64_t f = (S == R ? 1ull : 0ull) | (S == T ? 2ull : 0ull);
-                    if (j <= 32) flo |= f << (2 * (j - 1)); else fhi |= f << (2 * (j - 33));
-                    Sd = Su; Sl = S; Rl = R;
-                    So = S; To = T; bo = b;
-                }
-            }
-            int ti = m, tj = n, k = 0;                       // identical in every lane: the walk is warp-uniform
-            int64_t pos = J.op_off + m + n;
-            while (ti > 0 || tj > 0) {
-                int op;
-                if (ti == 0) op = 1;
-                else if (tj == 0) op = 2;
-                else {
-                    uint64_t w = __shfl_sync(FULLM, tj <= 32 ? flo : fhi, ti - 1);
-                    uint32_t f = (uint32_t)(w >> (2 * ((tj - 1) & 31))) & 3u;
-                    op = (f & 1u) ? 1 : ((f & 2u) ? 2 : 0);
-                }
-                --pos;
-                if (lane == 0) ops[pos] = (uint8_t)op;
-                k++;
-                if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
-            }
-            if (lane == 0) nops[job] = k;
+        if (m <= 0 || n <= 0) {                       // one empty side: all gaps (nw_alignment.cpp:61-74 with i or j at 0)
+            const int cnt = max(m, 0) + max(n, 0);
+            for (int t = lane; t < cnt; t += 32) ops[J.op_off + t] = (uint8_t)(m <= 0 ? 1 : 2);
+            if (lane == 0) nops[job] = cnt;
             continue;
         }
         const int wpr = (n + 15) >> 4;
         uint32_t *fl = flags + J.flag_off;
 
-        for (int s0 = 0; s0 < m; s0 += 32) {
-            const int i = s0 + lane + 1;              // my row (1-based)
-            const bool rowok = i <= m;
-            int a = rowok ? (int)codes[J.s1_off + i - 1] : 7;
-            a = (a & 4) ? 7 : (a & 3);                // 8..11 are lower-case ACGT: same base for the table compare
-            int Sl = -2 - i, Rl = NW_NEG;             // S[i][0], R[i][0]
-            int Sd = (i == 1) ? 0 : -2 - (i - 1);     // S[i-1][0]
-            int So = 0, To = 0, bo = 0;               // what I hand to the lane below
-            uint32_t fw = 0;
-            const int rows = min(32, m - s0);
-            const int steps = n + rows - 1;
-            const bool last_strip = s0 + 32 >= m;
+        // strips of NW_ROWS x 32 rows: lane l owns NW_ROWS consecutive rows and, at step t, column t - l + 1 of all of them
+        for (int s0 = 0; s0 < m; s0 += 32 * NW_ROWS) {
+            const int i0 = s0 + NW_ROWS * lane + 1;               // my first row (1-based)
+            int a[NW_ROWS], Sl[NW_ROWS], Rl[NW_ROWS];
+            uint32_t fw[NW_ROWS];
+#pragma unroll
+            for (int r = 0; r < NW_ROWS; r++) {
+                const int i = i0 + r;
+                int c = i <= m ? (int)codes[J.s1_off + i - 1] : 7;
+                a[r] = (c & 4) ? 7 : (c & 3);              // 8..11 are lower-case ACGT: same base for the table compare
+                Sl[r] = -2 - i; Rl[r] = NW_NEG; fw[r] = 0;  // S[i][0], R[i][0]
+            }
+            int Sd0 = (i0 == 1) ? 0 : -2 - (i0 - 1);       // S[i0-1][0]
+            int So = 0, To = 0, bo = 0;                    // what I hand to the lane below: my last row
+            const int rows = min(32 * NW_ROWS, m - s0);
+            const int lanes_used = (rows + NW_ROWS - 1) / NW_ROWS;
+            const int steps = n + lanes_used - 1;
+            const bool last_strip = s0 + 32 * NW_ROWS >= m;
             int bch = 0, such = 0, tuch = 0;
             for (int t = 0; t < steps; t++) {
                 if ((t & 31) == 0) {                  // fetch the next 32 columns of lane 0's inputs
@@ -126,24 +90,34 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
                 int Su = __shfl_up_sync(FULLM, So, 1);
                 int Tu = __shfl_up_sync(FULLM, To, 1);
                 int b = __shfl_up_sync(FULLM, bo, 1);
-                int b0 = __shfl_sync(FULLM, bch, t & 31);
-                int j = t - lane + 1;
+                const int b0 = __shfl_sync(FULLM, bch, t & 31);
+                const int j = t - lane + 1;
                 if (s0 > 0) {
-                    int su0 = __shfl_sync(FULLM, such, t & 31), tu0 = __shfl_sync(FULLM, tuch, t & 31);
+                    const int su0 = __shfl_sync(FULLM, such, t & 31), tu0 = __shfl_sync(FULLM, tuch, t & 31);
                     if (lane == 0) { Su = su0; Tu = tu0; }
                 } else if (lane == 0) { Su = -2 - j; Tu = NW_NEG; }
                 if (lane == 0) b = b0;
-                if (rowok && j >= 1 && j <= n) {
-                    int R = max(Rl - 1, Sl - 3);
-                    int T = max(Tu - 1, Su - 3);
-                    int h = max(Sd + (a == b ? 3 : -3), max(R, T));
-                    int S = (h / 2) * 2;
-                    uint32_t f = (S == R ? 1u : 0u) | (S == T ? 2u : 0u);
-                    fw |= f << (((j - 1) & 15) * 2);
-                    if (((j - 1) & 15) == 15 || j == n) { __stcg(fl + (size_t)(i - 1) * wpr + ((j - 1) >> 4), fw); fw = 0; }
-                    Sd = Su; Sl = S; Rl = R;
-                    So = S; To = T; bo = b;
-                    if (lane == 31 && !last_strip) { __stcg(rb + j, S); __stcg(rb + (n + 1) + j, T); }
+                if (i0 <= m && j >= 1 && j <= n) {
+                    int upS = Su, upT = Tu, diag = Sd0;
+                    const bool flush = ((j - 1) & 15) == 15 || j == n;
+                    const int fsh = ((j - 1) & 15) * 2;
+#pragma unroll
+                    for (int r = 0; r < NW_ROWS; r++) {
+                        if (i0 + r <= m) {
+                            const int R = max(Rl[r] - 1, Sl[r] - 3);
+                            const int T = max(upT - 1, upS - 3);
+                            const int h = max(diag + (a[r] == b ? 3 : -3), max(R, T));
+                            const int S = (h / 2) * 2;
+                            fw[r] |= ((S == R ? 1u : 0u) | (S == T ? 2u : 0u)) << fsh;
+                            if (flush) { __stcg(fl + (size_t)(i0 + r - 1) * wpr + ((j - 1) >> 4), fw[r]); fw[r] = 0; }
+                            diag = Sl[r];                  // S[i][j-1] is the diagonal of the row below
+                            Sl[r] = S; Rl[r] = R;
+                            upS = S; upT = T;
+                        }
+                    }
+                    Sd0 = Su;
+                    So = upS; To = upT; bo = b;            // my last valid row (the lane below only has rows if all of mine are valid)
+                    if (lane == 31 && !last_strip) { __stcg(rb + j, upS); __stcg(rb + (n + 1) + j, upT); }
                 }
             }
             __syncwarp();
@@ -154,7 +128,7 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
             // the current 16-column word and hand them round by shuffle; one reload every >= 16 steps instead of one
             // dependent L2 round trip per step (round-1 launch list of the 2x250 config: a 250 x 500 job spent ~3x longer
             // walking back through global memory on lane 0 than sweeping).
-            int ti = m, tj = n, k = 0;
+            int ti = m, tj = n, cnt = 0;
             int64_t pos = J.op_off + m + n;
             int base_i = -1, wcol = -1;
             uint32_t myw = 0;
@@ -175,10 +149,10 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
                 }
                 --pos;
                 if (lane == 0) ops[pos] = (uint8_t)op;
-                k++;
+                cnt++;
                 if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
             }
-            if (lane == 0) nops[job] = k;
+            if (lane == 0) nops[job] = cnt;
         }
         __syncwarp();
     }
