@@ -196,6 +196,9 @@ def main():
         run_reference_arm(args, rank)
         return
 
+    # many host threads per core (several contexts per GPU x several GPUs): wait for the GPU asleep, not spinning
+    if world * CONTEXTS >= (os.cpu_count() or 1):
+        os.environ.setdefault("DARTGPU_SYNC", "block")
     import torch
     import torch.distributed as dist
     from dart_b200 import capi
@@ -282,6 +285,7 @@ def main():
     M.map_reads(batch, True, False)
     M.map_reads(batch, True, False)
     alone = M.stats()
+    int32_peak = M.int32_peak()
     # kernel-only seeding over the whole batch on one context (no host orchestration, no copies): roofline of the dominant kernel
     M.seed_resident()
     ms_k = []
@@ -314,6 +318,7 @@ def main():
             "e2e": {"value": world * n_reads * args.steps / (ms_e2e * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
             "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS,
+            "host_sync": os.environ.get("DARTGPU_SYNC", "spin"), "host_cores": os.cpu_count(),
             "roofline": {"bound": "hbm", "kernel": "k_search (FM-index forward extension)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -327,6 +332,12 @@ def main():
             "nw_gcups": (alone["nw_cells"] / (alone["ms_nw"] * 1e-3) / 1e9) if alone["ms_nw"] > 0 else None,
             "seed_gbs": achieved,
         }
+        if line["nw_gcups"]:
+            ops_per_cell = 22    # adds, max and compares of the restated recurrence + traceback flags (nw_kernel.cu), per cell
+            line["nw_roofline"] = {"bound": "int32", "achieved_gcups": line["nw_gcups"], "int32_ops_per_s_measured": int32_peak,
+                                   "ops_per_cell": ops_per_cell, "peak_gcups": int32_peak / ops_per_cell / 1e9,
+                                   "frac": line["nw_gcups"] * 1e9 * ops_per_cell / int32_peak,
+                                   "note": "whole NW stage of one context alone (shape sort + both kernels + tracebacks), cells = sum of m*n"}
         if world == 1:
             try:
                 cores = os.cpu_count() or 1

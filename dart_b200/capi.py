@@ -77,7 +77,7 @@ EXPORTS = ["dartgpu_default_params", "dartgpu_create", "dartgpu_create_from_file
            "dartgpu_sequence_name", "dartgpu_sequence_length", "dartgpu_set_stream", "dartgpu_seed_and_cluster",
            "dartgpu_kmer_reseed", "dartgpu_nw_align", "dartgpu_map_reads", "dartgpu_get_stats",
            "dartgpu_upload_reads", "dartgpu_seed_and_cluster_resident", "dartgpu_synchronize",
-           "dartgpu_map_reads_resident", "dartgpu_index_build"]
+           "dartgpu_map_reads_resident", "dartgpu_index_build", "dartgpu_measure_int32_peak"]
 
 
 def load_library() -> C.CDLL:
@@ -196,6 +196,12 @@ class Mapper:
         s = Stats()
         self.L.dartgpu_get_stats(self.h, C.byref(s))
         return s.as_dict()
+
+    def int32_peak(self) -> float:
+        """Measured INT32 add/max operations per second of this GPU (the NW kernels' roofline denominator)."""
+        v = C.c_double(0)
+        self._check(self.L.dartgpu_measure_int32_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     # ---- IdentifySeedPairs + GenerateAlignmentCandidate ----
     def identify_seed_pairs(self, reads: ReadBatch) -> dict:

@@ -159,7 +159,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     DG_CUDA(cudaEventRecord(c->ev[3], st));
     launch_scan_hits(a, c->d_scan_tmp.p, tmp, st);
     DG_CUDA(cudaMemcpyAsync(c->h_total.p, c->d_seed_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     const int64_t total = c->h_total.p[0];
     c->total_seeds = total;
     c->stats.kernel_launches += 2;
@@ -198,7 +198,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     }
     DG_CUDA(cudaMemcpyAsync(c->h_dstats.p, c->d_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaEventRecord(c->ev[7], st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     add_ms(c, &c->stats.ms_h2d, c->ev[0], c->ev[1]);
     add_ms(c, &c->stats.ms_search, c->ev[2], c->ev[3]);
     add_ms(c, &c->stats.ms_locate, c->ev[4], c->ev[5]);
@@ -259,7 +259,7 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[9], st));
     DG_CUDA(cudaMemcpyAsync(c->h_khits.p, c->d_khits.p, (size_t)n_jobs * sizeof(dartgpu_kmer_hit), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
     c->stats.kernel_launches += KMER_LAUNCHES;
     c->stats.kmer_jobs += n_jobs;
@@ -298,7 +298,7 @@ void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs
     DG_CUDA(cudaEventRecord(c->ev[11], st));
     DG_CUDA(cudaMemcpyAsync(c->h_nw_ops.p, c->d_nw_ops.p, ops_total, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(c->h_nw_nops.p, c->d_nw_nops.p, (size_t)n_jobs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
     c->stats.kernel_launches += NW_LAUNCHES;
     c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(NwJobDev);
@@ -416,7 +416,7 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
         S->d_occ32.reserve(occ_bytes);
         launch_relayout_occ32(raw.p, n_words, reinterpret_cast<Occ32 *>(S->d_occ32.p), n_blocks32, st);
         DG_CUDA(cudaGetLastError());
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(dg_stream_sync(st));
     }
     ix.occ32 = reinterpret_cast<const Occ32 *>(S->d_occ32.p);
     {
@@ -427,7 +427,7 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
         ix.sa = S->d_sa.p;
         launch_sa_densify(ix, sa_file.p, v->sa_intv, v->n_sa, S->d_sa.p, st);
         DG_CUDA(cudaGetLastError());
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(dg_stream_sync(st));
     }
     {   // search-start table: K = floor(log4(text length)) - 1 (most K-mers of a read occur), at most 13 (1 GB);
         // DARTGPU_KTAB=<K> overrides, 0 disables
@@ -442,7 +442,7 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
             S->d_ktab.reserve(n_ent); tmp.reserve(n_ent);
             launch_build_ktab(ix, K, S->d_ktab.p, tmp.p, st);
             DG_CUDA(cudaGetLastError());
-            DG_CUDA(cudaStreamSynchronize(st));
+            DG_CUDA(dg_stream_sync(st));
             ix.ktab = S->d_ktab.p; ix.ktab_k = K;
         }
     }
@@ -454,11 +454,11 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
         S->d_ref2.reserve(ref_words);
         launch_build_ref2(dpac.p, S->d_ref2.p, S->G, st);
         DG_CUDA(cudaGetLastError());
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(dg_stream_sync(st));
     }
     S->d_ends.reserve(S->ends.size());
     DG_CUDA(cudaMemcpyAsync(S->d_ends.p, S->ends.data(), S->ends.size() * 8, cudaMemcpyHostToDevice, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     ix.ref2 = S->d_ref2.p; ix.chr_ends = S->d_ends.p;
     g_indexes[key] = S;
     return S;
@@ -487,7 +487,7 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
     c->ix = c->shared->ix;
     c->G = c->shared->G;
     c->d_stats.reserve(1); c->h_total.reserve(2); c->h_dstats.reserve(1); c->d_steal.reserve(4);
-    DG_CUDA(cudaStreamSynchronize(c->stream));
+    DG_CUDA(dg_stream_sync(c->stream));
 }
 
 static bool slurp(const std::string &fn, std::vector<uint8_t> &buf)
@@ -639,7 +639,7 @@ int dartgpu_seed_and_cluster(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu
 int dartgpu_upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
 {
     if (!c || !reads) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
-    return guarded(c, [&] { stats_begin(c); upload_reads(c, reads); DG_CUDA(cudaStreamSynchronize(c->stream)); });
+    return guarded(c, [&] { stats_begin(c); upload_reads(c, reads); DG_CUDA(dg_stream_sync(c->stream)); });
 }
 
 int dartgpu_seed_and_cluster_resident(dartgpu_ctx *c)
@@ -656,7 +656,7 @@ int dartgpu_seed_and_cluster_resident(dartgpu_ctx *c)
 int dartgpu_synchronize(dartgpu_ctx *c)
 {
     if (!c) return DARTGPU_ERR_ARG;
-    return guarded(c, [&] { DG_CUDA(cudaStreamSynchronize(c->stream)); });
+    return guarded(c, [&] { DG_CUDA(dg_stream_sync(c->stream)); });
 }
 
 int dartgpu_kmer_reseed(dartgpu_ctx *c, const char *bases, int64_t n_bases, const dartgpu_kmer_job *jobs, int32_t n_jobs,
@@ -732,6 +732,12 @@ int dartgpu_map_reads_resident(dartgpu_ctx *c, const dartgpu_reads *reads, dartg
         c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_report;
         c->stats.ms_host = t.ms();
     });
+}
+
+int dartgpu_measure_int32_peak(dartgpu_ctx *c, double *ops_per_second)
+{
+    if (!c || !ops_per_second) return DARTGPU_ERR_ARG;
+    return guarded(c, [&] { *ops_per_second = measure_int32_ops_per_second(c->stream); });
 }
 
 int dartgpu_get_stats(const dartgpu_ctx *c, dartgpu_stats *out)

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -99,6 +101,27 @@ template <class T> struct PinBuf {
     ~PinBuf() { release(); }
 };
 
+// Host-side wait for a stream.  By default the driver spins, which is the lowest latency while every waiting host thread has
+// a core of its own; with DARTGPU_SYNC=block the thread sleeps on a blocking event instead, so that many contexts (several
+// per GPU x 8 GPUs on a 16-core host) do not steal the cores the other threads need to launch their kernels.
+inline cudaError_t dg_stream_sync(cudaStream_t st)
+{
+    static const bool block = [] { const char *e = getenv("DARTGPU_SYNC"); return e && !strcmp(e, "block"); }();
+    if (!block) return cudaStreamSynchronize(st);
+    thread_local cudaEvent_t ev = nullptr;
+    thread_local int ev_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!ev || ev_dev != dev) {
+        if (ev) cudaEventDestroy(ev);
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ev = nullptr; return e; }
+        ev_dev = dev;
+    }
+    cudaError_t e = cudaEventRecord(ev, st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ev);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // kernel launchers (each file owns its kernels; all work is enqueued on `st`)
 // ---------------------------------------------------------------------------------------------------
@@ -146,6 +169,7 @@ constexpr int NW_LAUNCHES = 4;     // sort keys, radix sort (counted once), k_nw
 void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,
                uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, NwScratch &scratch, cudaStream_t st);
 int nw_grid_warps();
+double measure_int32_ops_per_second(cudaStream_t st);
 
 // kmer_kernel.cu
 struct KmerJobDev { int64_t s1_off; int64_t gpos; int32_t len1, len2; };

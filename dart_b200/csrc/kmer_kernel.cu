@@ -408,7 +408,7 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
     launch_scan_u32_to_i64(S.ntiles.p, S.tile_off.p, n_jobs, S.scan_tmp.p, tmp, st);
     launch_scan_u32_to_i64(S.cap.p, S.rec_off.p, n_jobs, S.scan_tmp.p, tmp, st);
     DG_CUDA(cudaMemcpyAsync(S.h_total.p, S.rec_off.p + n_jobs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     S.recs.reserve((size_t)S.h_total.p[0] + 1);
     k_kmer_scan<<<148 * 8, KS_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, S.tile_off.p, S.rec_off.p, S.cap.p, S.count.p, S.recs.p);
     k_kmer_walk<<<n_jobs < 148 * 16 ? n_jobs : 148 * 16, 128, 0, st>>>(jobs, n_jobs, S.rec_off.p, S.cap.p, S.count.p, S.recs.p,

@@ -239,6 +239,42 @@ k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__re
     }
 }
 
+// INT32 pipe microbenchmark for the NW roofline: 8 independent add/max chains per thread (the recurrence's operation
+// mix), every SM full.  Returns integer add/max operations per second (SURVEY.md §8d asks for a measured peak, not the
+// spec sheet).
+__global__ void __launch_bounds__(256) k_int32_peak(int *out, int iters, int seed)
+{
+    int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const int b = seed + blockIdx.x, c = seed - 3;
+    for (int i = 0; i < iters; i++) {
+        a0 = max(a0 + b, a1); a1 = max(a1 + c, a2); a2 = max(a2 + b, a3); a3 = max(a3 + c, a4);
+        a4 = max(a4 + b, a5); a5 = max(a5 + c, a6); a6 = max(a6 + b, a7); a7 = max(a7 + c, a0);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+double measure_int32_ops_per_second(cudaStream_t st)
+{
+    const int grid = 148 * 8, iters = 1 << 14;
+    DevBuf<int> out;
+    out.reserve((size_t)grid * 256);
+    cudaEvent_t e0, e1;
+    DG_CUDA(cudaEventCreate(&e0)); DG_CUDA(cudaEventCreate(&e1));
+    k_int32_peak<<<grid, 256, 0, st>>>(out.p, iters, 1);                 // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        DG_CUDA(cudaEventRecord(e0, st));
+        k_int32_peak<<<grid, 256, 0, st>>>(out.p, iters, rep + 2);
+        DG_CUDA(cudaEventRecord(e1, st));
+        DG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        DG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return (double)grid * 256 * iters * 16.0 / (best * 1e-3);            // 8 adds + 8 max per iteration
+}
+
 int nw_grid_warps() { return 148 * 8 * (NW_THREADS / 32); }
 
 void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,

@@ -287,7 +287,7 @@ static void scan_u32(dartgpu_ctx *c, DevicePipe *D, const uint32_t *in, int64_t 
 static int64_t fetch_i64(dartgpu_ctx *c, DevicePipe *D, const int64_t *dev)
 {
     DG_CUDA(cudaMemcpyAsync(D->h_vals.p, dev, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    DG_CUDA(cudaStreamSynchronize(c->stream));
+    DG_CUDA(dg_stream_sync(c->stream));
     return D->h_vals.p[0];
 }
 
@@ -309,7 +309,7 @@ static void nw_round(dartgpu_ctx *c, DevicePipe *D, NwJobDev *jobs, int nj, bool
     DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 1, D->scan_b.p + nj, 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 2, D->scan_c.p + nj, 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     const int64_t ops_total = D->h_vals.p[0], flag_total = D->h_vals.p[1], aux_total = D->h_vals.p[2];
     const int max_n = D->h_counters.p[0];
     const bool multi = D->h_counters.p[1] != 0;
@@ -321,7 +321,7 @@ static void nw_round(dartgpu_ctx *c, DevicePipe *D, NwJobDev *jobs, int nj, bool
     launch_nw(c->ix, c->d_codes.p, jobs, nj, D->flags.p, D->rowbuf.p, rb, ops.p, nops.p, c->nwscratch, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[11], st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
     c->stats.kernel_launches += 4 + NW_LAUNCHES;
     c->stats.nw_jobs += nj;
@@ -342,7 +342,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
         DG_CUDA(cudaMemcpyAsync(D->d_chr_fwd.p, c->shared->chr_fwd.data(), c->shared->chr_fwd.size() * 8, cudaMemcpyHostToDevice, st));
         std::vector<int32_t> ec(c->shared->end_chr.begin(), c->shared->end_chr.end());
         DG_CUDA(cudaMemcpyAsync(D->d_end_chr.p, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice, st));
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(dg_stream_sync(st));
         D->tables = true;
     }
     if (n == 0) { *out = dartgpu_map_result{nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0}; return; }
@@ -385,7 +385,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     k_phase<0><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     const int nk = D->h_counters.p[0];
     if (nk > 0) {
         DG_CUDA(cudaEventRecord(c->ev[8], st));
@@ -393,7 +393,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
         launch_kmer(c->ix, c->d_codes.p, D->kjobs.p, nk, std::max(c->max_rlen, 8), D->khits.p, c->kscratch, st);
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaEventRecord(c->ev[9], st));
-        DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(dg_stream_sync(st));
         add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
         c->stats.kernel_launches += KMER_LAUNCHES;
     }
@@ -404,7 +404,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     k_phase<1><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     const int nB = D->h_counters.p[0];
     nw_round(c, D, D->jobsB.p, nB, true, D->opsB, D->nopsB);
 
@@ -414,7 +414,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     k_phase<2><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     const int nC = D->h_counters.p[0];
     nw_round(c, D, D->jobsC.p, nC, false, D->opsC, D->nopsC);
 
@@ -445,7 +445,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 0, D->text_off.p + nrep, 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 1, D->junc_off.p + n, 8, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 6, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     const int64_t text_total = D->h_vals.p[0], junc_total = D->h_vals.p[1];
     if (D->h_counters.p[0]) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("CIGAR pool capacity exceeded"));
     D->text.reserve(text_total + 1); D->junc.reserve(junc_total + 1);
@@ -462,7 +462,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     if (junc_total) DG_CUDA(cudaMemcpyAsync(D->h_junc.p, D->junc.p, (size_t)junc_total * sizeof(dartgpu_junction), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_work.p, D->work.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaEventRecord(c->ev[14], st));
-    DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(dg_stream_sync(st));
     c->stats.nw_cells += D->h_work.p[0]; c->stats.kmer_window_bases += D->h_work.p[1]; c->stats.kmer_read_bases += D->h_work.p[2];
     add_ms(c, &c->stats.ms_report, c->ev[12], c->ev[13]);
     add_ms(c, &c->stats.ms_d2h, c->ev[13], c->ev[14]);

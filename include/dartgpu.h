@@ -201,6 +201,9 @@ typedef struct {
 } dartgpu_stats;
 
 int dartgpu_get_stats(const dartgpu_ctx *ctx, dartgpu_stats *out);
+/* INT32 add/max operations per second of the context's GPU, measured with a saturating microbenchmark: the denominator
+ * of the NW kernels' integer roofline. */
+int dartgpu_measure_int32_peak(dartgpu_ctx *ctx, double *ops_per_second);
 
 /* Device-resident variant of stage 1 for kernel-only timing: upload once, run the seeding kernels many times
  * without any host<->device copy in between (bench.py `value`). */

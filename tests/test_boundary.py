@@ -13,7 +13,7 @@ from dart_b200 import capi
 def test_library_exports_every_declared_symbol():
     L = capi.load_library()
     header = open(os.path.join(ROOT, "include", "dartgpu.h")).read()
-    declared = set(re.findall(r"\b(dartgpu_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(dartgpu_[a-z0-9_]+)\s*\(", header))
     assert declared == set(capi.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
@@ -45,3 +45,20 @@ def test_missing_index_is_reported():
     with pytest.raises(capi.DartGpuError) as e:
         capi.Mapper("/nonexistent/prefix")
     assert e.value.code == -3
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-device error path")
+def test_index_build_refuses_without_a_device(tmp_path):
+    from dart_b200 import synth
+    g = synth.random_genome(5000, 1, seed=3)
+    with pytest.raises(capi.DartGpuError) as e:
+        capi.index_build(g, str(tmp_path / "idx"))
+    assert e.value.code == -1 and "no CPU fallback" in str(e.value)
+    assert not os.path.exists(tmp_path / "idx.bwt")           # nothing half-written
+
+
+def test_index_build_rejects_bad_arguments():
+    L = capi.load_library()
+    assert L.dartgpu_index_build(0, None, 100, b"/tmp/x", 0) == -4
+    buf = (C.c_uint8 * 8)()
+    assert L.dartgpu_index_build(0, buf, 0, b"/tmp/x", 0) == -4
