@@ -196,8 +196,14 @@ def main():
         run_reference_arm(args, rank)
         return
 
-    # many host threads per core (several contexts per GPU x several GPUs): wait for the GPU asleep, not spinning
-    if world * CONTEXTS >= (os.cpu_count() or 1):
+    # One host thread per context, and a thread that waits for its stream spins (lowest latency; measured at 2 GPUs: waiting
+    # on a blocking event instead costs 23 % of `value`).  So the contexts of all ranks together must not exceed the host's
+    # cores: 4 per GPU up to 4 GPUs on this 16-core box, 2 per GPU at 8.  Only if even one context per GPU does not fit
+    # do the threads wait asleep (DARTGPU_SYNC=block).
+    global CONTEXTS
+    cores_total = os.cpu_count() or 1
+    CONTEXTS = max(1, min(CONTEXTS, cores_total // world))
+    if world * CONTEXTS > cores_total:
         os.environ.setdefault("DARTGPU_SYNC", "block")
     import torch
     import torch.distributed as dist

@@ -207,18 +207,26 @@ k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__re
             a = (a & 4) ? 7 : (a & 3);
             int Sl = -2 - i, Rl = NWT_NEG, Sd = sS[0][tid];
             sS[0][tid] = (int16_t)Sl;
-            uint32_t fw = 0;
-            for (int j = 1; j <= n; j++) {
-                const int Su = sS[j][tid], Tu = sT[j][tid];
-                const int b = (int)(((j <= 32 ? g0 >> (2 * (j - 1)) : g1 >> (2 * (j - 33)))) & 3);
-                const int R = max(Rl - 1, Sl - 3);
-                const int T = max(Tu - 1, Su - 3);
-                const int h = max(Sd + (a == b ? 3 : -3), max(R, T));
-                const int S = (h / 2) * 2;
-                fw |= ((S == R ? 1u : 0u) | (S == T ? 2u : 0u)) << (((j - 1) & 15) * 2);
-                if (((j - 1) & 15) == 15 || j == n) { fl[(size_t)(i - 1) * wpr + ((j - 1) >> 4)] = fw; fw = 0; }
-                Sd = Su; Sl = S; Rl = R;
-                sS[j][tid] = (int16_t)S; sT[j][tid] = (int16_t)T;
+            // 16 columns at a time: their genome bases in one 32-bit word (shifted out two bits per column), their
+            // traceback flags in another (shifted in), one store per group
+            for (int jg = 0; jg < wpr; jg++) {
+                uint32_t gw = jg == 0 ? (uint32_t)g0 : jg == 1 ? (uint32_t)(g0 >> 32) : jg == 2 ? (uint32_t)g1 : (uint32_t)(g1 >> 32);
+                uint32_t fw = 0;
+                const int j0 = 16 * jg + 1, cols = min(16, n - 16 * jg);
+                for (int c = 0; c < cols; c++) {
+                    const int j = j0 + c;
+                    const int Su = sS[j][tid], Tu = sT[j][tid];
+                    const int b = (int)(gw & 3u);
+                    gw >>= 2;
+                    const int R = max(Rl - 1, Sl - 3);
+                    const int T = max(Tu - 1, Su - 3);
+                    const int h = max(Sd + (a == b ? 3 : -3), max(R, T));
+                    const int S = (h / 2) * 2;
+                    fw |= ((S == R ? 1u : 0u) | (S == T ? 2u : 0u)) << (2 * c);
+                    Sd = Su; Sl = S; Rl = R;
+                    sS[j][tid] = (int16_t)S; sT[j][tid] = (int16_t)T;
+                }
+                fl[(size_t)(i - 1) * wpr + jg] = fw;
             }
         }
         int ti = m, tj = n, cnt = 0;
