@@ -244,7 +244,7 @@ def main():
     subs = []
     for a, b in zip(bounds[:-1], bounds[1:]):
         off = batch.offsets[a:b + 1]
-        subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]], (off - off[0]).copy()))
+        subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]].copy(), (off - off[0]).copy()).pin())   # e2e: inputs in pinned host memory
     pool = ThreadPoolExecutor(CONTEXTS)
 
     def run_steps(resident, steps):

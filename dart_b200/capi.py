@@ -144,6 +144,16 @@ class ReadBatch:
     def n(self) -> int:
         return len(self.offsets) - 1
 
+    def pin(self) -> "ReadBatch":
+        """The same batch in page-locked host memory (torch's pinned allocator): dartgpu_map_reads hands page-locked
+        caller buffers straight to the DMA engine instead of staging them through its own pinned buffer."""
+        import torch
+        tb = torch.from_numpy(np.ascontiguousarray(self.bases, dtype=np.uint8)).pin_memory()
+        to = torch.from_numpy(np.ascontiguousarray(self.offsets, dtype=np.int64)).pin_memory()
+        out = ReadBatch(tb.numpy(), to.numpy())
+        out._keep = (tb, to)
+        return out
+
     def _c(self) -> _Reads:
         self.bases = np.ascontiguousarray(self.bases, dtype=np.uint8)
         self.offsets = np.ascontiguousarray(self.offsets, dtype=np.int64)

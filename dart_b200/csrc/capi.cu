@@ -104,17 +104,31 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
     cudaStream_t st = c->stream;
     DG_CUDA(cudaEventRecord(c->ev[0], st));
     if (n) {
-        // The caller's buffers are pageable: stage them through pinned memory in slices, every core copying, and hand
-        // each slice to the DMA engine as soon as it is staged so the host copy of slice k+1 overlaps the transfer of k.
-        memcpy(c->h_off.p, reads->offsets, (size_t)(n + 1) * sizeof(int64_t));
-        DG_CUDA(cudaMemcpyAsync(c->d_off.p, c->h_off.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        const int64_t slice = 16 << 20, piece = 1 << 20;
-        for (int64_t s0 = 0; s0 < n_bases; s0 += slice) {
-            const int64_t len = std::min(slice, n_bases - s0), npieces = (len + piece - 1) / piece;
+        // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister) are handed to the DMA engine as they
+        // are.  Pageable ones are staged through pinned memory in slices, every core copying, each slice handed over as soon
+        // as it is staged so the host copy of slice k+1 overlaps the transfer of k.
+        auto pinned = [](const void *p) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            return at.type == cudaMemoryTypeHost;
+        };
+        if (pinned(reads->offsets))
+            DG_CUDA(cudaMemcpyAsync(c->d_off.p, reads->offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        else {
+            memcpy(c->h_off.p, reads->offsets, (size_t)(n + 1) * sizeof(int64_t));
+            DG_CUDA(cudaMemcpyAsync(c->d_off.p, c->h_off.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        }
+        if (pinned(reads->bases + first))
+            DG_CUDA(cudaMemcpyAsync(c->d_raw.p, reads->bases + first, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+        else {
+            const int64_t slice = 16 << 20, piece = 1 << 20;
+            for (int64_t s0 = 0; s0 < n_bases; s0 += slice) {
+                const int64_t len = std::min(slice, n_bases - s0), npieces = (len + piece - 1) / piece;
 #pragma omp parallel for schedule(static) num_threads(threads)
-            for (int64_t k = 0; k < npieces; k++)
-                memcpy(c->h_raw.p + s0 + k * piece, reads->bases + first + s0 + k * piece, (size_t)std::min(piece, len - k * piece));
-            DG_CUDA(cudaMemcpyAsync(c->d_raw.p + s0, c->h_raw.p + s0, (size_t)len, cudaMemcpyHostToDevice, st));
+                for (int64_t k = 0; k < npieces; k++)
+                    memcpy(c->h_raw.p + s0 + k * piece, reads->bases + first + s0 + k * piece, (size_t)std::min(piece, len - k * piece));
+                DG_CUDA(cudaMemcpyAsync(c->d_raw.p + s0, c->h_raw.p + s0, (size_t)len, cudaMemcpyHostToDevice, st));
+            }
         }
         launch_read_layout(c->d_off.p, n, c->d_rlen.p, c->d_padded.p, st);
         size_t tmp = scan_tmp_bytes(n);
