@@ -26,6 +26,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "dartgpu_internal.h"
 #include "rank.cuh"
@@ -98,25 +99,116 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     const int K = ix.ktab ? ix.ktab_k : 0;
     const uint32_t kmask2 = K >= 16 ? ~0u : (1u << (2 * K)) - 1u, kmask1 = (1u << K) - 1u;
 
-    bool own = true, have_read = false, searching = false, finished = false, ended = false;
+    // A lane is in one of four states.  STEP: one rank step per iteration.  JUMP: the search has a start whose first K bases
+    // can be looked up in the search-start table; the lookup is ONE 256-bit load like a rank step's and rides the same load
+    // instruction, so its latency is hidden exactly like a step's.  NEED: the read is exhausted; fetching the next one
+    // (two atomics' worth of hand-out and a chain of dependent loads) is the only long turn-around left, and lanes wait
+    // until at least TURN_BATCH of them need it (or nobody is stepping) so that the warp pays for it together.
+    // Everything else a finished segment needs — record it, advance the start, skip ambiguous bases, cut the next K-mer
+    // out of the packed read — is register arithmetic and runs at once.
+    // History (ncu, round 1): with the whole turn-around inline 14 of 32 lanes were active; batching all of it (start-table
+    // gather included) cut the time by a quarter but left lanes waiting 60 % of the iterations, because after every
+    // mismatch a read goes through several searches of only 2-4 steps.
+    enum { ST_STEP = 0, ST_JUMP = 1, ST_NEED = 2, ST_DONE = 3 };
+    const char *ktab = reinterpret_cast<const char *>(ix.ktab);
+    const int TURN_BATCH = a.turn_batch;
+    bool own = true, have_read = false;
+    int st = ST_NEED;
     int r = 0, rl = 0, start = 0, p = 0, cw = -1;
     int64_t wbase = 0;
-    uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0;
+    uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0, kidx = 0;
     IdxT x1 = 0;
     uint32_t st_steps = 0, st_splits = 0;
 
-    // Two kinds of work alternate in a lane: rank steps (the hot path) and, every ~20 steps, the "turn-around" — record
-    // the finished segment, find the next search start or the next read, gather the K-mer start.  ncu of the first
-    // thread-per-chain version: 14 of 32 lanes active on average, because at almost every iteration SOME lane was in its
-    // turn-around and the warp executed both paths.  Lanes now wait for company: the turn-around runs only when at least
-    // TURN_BATCH lanes need it (or nobody is stepping), so its ~100 instructions are shared by several lanes.
-    constexpr int TURN_BATCH = 6;
+    // next search start of the current read: skip ambiguous bases, then either a table lookup (JUMP) or the reference's
+    // single-base start (STEP); NEED when the read has no start left (IdentifySeedPairs' `pos < rlen - 13`)
+    auto advance = [&]() {
+        while (start < rl - 13) {              // a search cannot start on an ambiguous base
+            if ((start >> 4) != cw) { cw = start >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+            if (!((wamb >> (start & 15)) & 1u)) break;
+            start++;
+        }
+        if (start >= rl - 13) { st = ST_NEED; return; }
+        if (K > 0 && start + K <= rl) {
+            const int sh = start & 15;
+            uint32_t bits = wcode >> (2 * sh), ambs = wamb >> sh;
+            if (sh + K > 16) {
+                const uint2 w2 = __ldg(a.packed + wbase + cw + 1);
+                bits |= sh ? w2.x << (32 - 2 * sh) : 0u; ambs |= w2.y << (16 - sh);
+            }
+            if ((ambs & kmask1) == 0) { kidx = bits & kmask2; st = ST_JUMP; return; }
+        }
+        const int c0 = (wcode >> ((start & 15) * 2)) & 3;
+        x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
+        p = start + 1;
+        st = ST_STEP;
+    };
+
     for (;;) {
-        const unsigned need_m = __ballot_sync(FULL, !searching && !finished);
-        const unsigned step_m = __ballot_sync(FULL, searching);
-        if ((need_m | step_m) == 0) break;
-        if (!searching && !finished && (__popc(need_m) >= TURN_BATCH || step_m == 0)) {
-            if (ended) {                                  // the segment that just ended: bwt_search.cpp:173, IdentifySeedPairs' advance
+        const unsigned need_m = __ballot_sync(FULL, st == ST_NEED);
+        const unsigned act_m = __ballot_sync(FULL, st == ST_STEP || st == ST_JUMP);
+        if ((need_m | act_m) == 0) break;
+        if (st == ST_NEED && (__popc(need_m) >= TURN_BATCH || act_m == 0)) {
+            if (have_read) { a.nrec[r] = nr; a.nhits[r] = nh; have_read = false; }
+            if (own) { r = atomicAdd(&s_next, 1); if (r >= r_end) own = false; }
+            if (!own) r = a.steal_base + (int)atomicAdd(a.steal, 1u);
+            if (r >= a.n_reads) st = ST_DONE;
+            else {
+                rl = a.rlen[r];
+                wbase = a.dev_off[r] >> 4;
+                start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
+                advance();
+            }
+        }
+        if (st == ST_STEP || st == ST_JUMP) {
+            const bool stepping = st == ST_STEP;
+            bool end = false, two = false;
+            const char *addr0 = ktab + (size_t)(kidx >> 1) * 32, *addr1 = addr0;
+            IdxT kk = 0, ll = 0;
+            int c = 0;
+            if (stepping) {
+                end = p >= rl;
+                if (!end) {
+                    if ((p >> 4) != cw) { cw = p >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+                    end = (wamb >> (p & 15)) & 1u;
+                }
+                if (!end) {
+                    const IdxT k = x1 - 1, l = k + x2;
+                    kk = k - (k >= primary); ll = l - (l >= primary);
+                    c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3u);       // complement: backward step of revcomp(P)
+                    const uint64_t bk = (uint64_t)kk >> 6, bl = (uint64_t)ll >> 6;
+                    addr0 = occ + bk * 32; addr1 = occ + bl * 32;
+                    two = bl != bk;                                       // narrow intervals sit in one block: one load
+                }
+            }
+            if (!end) {
+                const OccBlock B0 = load_block(addr0, 0);
+                OccBlock B1 = B0;
+                if (two) B1 = load_block(addr1, 0);
+                if (stepping) {
+                    const uint32_t ok = block_rank(B0, (uint32_t)kk & 63u, c), ol = block_rank(B1, (uint32_t)ll & 63u, c);
+                    st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
+                    const uint32_t n2 = ol - ok;
+                    if (n2 == 0) end = true;
+                    else { x1 = (IdxT)s_L2[c] + 1 + ok; x2 = n2; p++; }
+                } else {
+                    // the 32-byte load holds two 16-byte KmerStart entries: {u64 x1, u32 x2, u32 splits}
+                    const bool hi = kidx & 1u;
+                    const uint64_t e_x1 = hi ? B0.lo : ((uint64_t)B0.cnt[1] << 32 | B0.cnt[0]);
+                    const uint32_t e_x2 = hi ? (uint32_t)B0.hi : B0.cnt[2];
+                    const uint32_t e_sp = hi ? (uint32_t)(B0.hi >> 32) : B0.cnt[3];
+                    if (e_x2 != 0) {
+                        x1 = (IdxT)e_x1; x2 = e_x2; p = start + K;
+                        st_steps += K - 1; st_splits += e_sp;
+                    } else {                        // the K-mer does not occur: start from the single base as the reference does
+                        const int c0 = (int)(kidx & 3u);
+                        x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
+                        p = start + 1;
+                    }
+                    st = ST_STEP;
+                }
+            }
+            if (end) {                                   // bwt_search.cpp:173 and IdentifySeedPairs' advance
                 const int len = p - start;
                 if (x2 <= a.max_dup && len >= 16) {
                     if ((int)nr < a.cap_rec) {
@@ -126,80 +218,11 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                     nr++; nh += x2;
                     start += len;
                 } else start++;
-                ended = false;
+                advance();
             }
-            for (;;) {
-                if (!have_read) {
-                    if (own) { r = atomicAdd(&s_next, 1); if (r >= r_end) own = false; }
-                    if (!own) { r = a.steal_base + (int)atomicAdd(a.steal, 1u); if (r >= a.n_reads) { finished = true; break; } }
-                    rl = a.rlen[r];
-                    wbase = a.dev_off[r] >> 4;
-                    start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
-                }
-                while (start < rl - 13) {              // a search cannot start on an ambiguous base
-                    if ((start >> 4) != cw) { cw = start >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
-                    if (!((wamb >> (start & 15)) & 1u)) break;
-                    start++;
-                }
-                if (start < rl - 13) break;
-                a.nrec[r] = nr; a.nhits[r] = nh;
-                have_read = false;
-            }
-            if (!finished) {
-                // the first K bases of the search in one gather (KmerStart), when they are all inside the read, unambiguous
-                // and the K-mer occurs; otherwise start from the single base as the reference does
-                bool jumped = false;
-                if (K > 0 && start + K <= rl) {
-                    const int sh = start & 15;
-                    uint32_t bits = wcode >> (2 * sh), ambs = wamb >> sh;
-                    if (sh + K > 16) {
-                        const uint2 w2 = __ldg(a.packed + wbase + cw + 1);
-                        bits |= sh ? w2.x << (32 - 2 * sh) : 0u; ambs |= w2.y << (16 - sh);
-                    }
-                    if ((ambs & kmask1) == 0) {
-                        const KmerStart e = ix.ktab[bits & kmask2];
-                        if (e.x2 != 0) {
-                            x1 = (IdxT)e.x1; x2 = e.x2; p = start + K;
-                            st_steps += K - 1; st_splits += e.splits;
-                            jumped = true;
-                        }
-                    }
-                }
-                if (!jumped) {
-                    const int c0 = (wcode >> ((start & 15) * 2)) & 3;
-                    x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
-                    p = start + 1;
-                }
-                searching = true;
-            }
-        }
-        if (searching) {
-            bool end = p >= rl;
-            if (!end) {
-                if ((p >> 4) != cw) { cw = p >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
-                end = (wamb >> (p & 15)) & 1u;
-            }
-            if (!end) {
-                const IdxT k = x1 - 1, l = k + x2;
-                const IdxT kk = k - (k >= primary), ll = l - (l >= primary);
-                const int c = 3 - (int)((wcode >> ((p & 15) * 2)) & 3u);     // complement: backward step of revcomp(P)
-                const uint64_t bk = (uint64_t)kk >> 6, bl = (uint64_t)ll >> 6;
-                const OccBlock Bk = load_block(occ, bk);
-                OccBlock Bl = Bk;
-                if (bl != bk) Bl = load_block(occ, bl);                      // narrow intervals sit in one block: one load
-                const uint32_t ok = block_rank(Bk, (uint32_t)kk & 63u, c), ol = block_rank(Bl, (uint32_t)ll & 63u, c);
-                st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
-                const uint32_t n2 = ol - ok;
-                if (n2 == 0) end = true;
-                else {
-                    x1 = (IdxT)s_L2[c] + 1 + ok;
-                    x2 = n2;
-                    p++;
-                }
-            }
-            if (end) { searching = false; ended = true; }
         }
     }
+    if (have_read) { a.nrec[r] = nr; a.nhits[r] = nh; }
     __syncwarp();
     const unsigned long long ws = warp_sum(st_steps), wp = warp_sum(st_splits);
     if ((threadIdx.x & 31) == 0 && ws) {
@@ -229,6 +252,8 @@ void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
     // 3/4 of the batch is split statically between the CTAs, the last quarter is stolen read by read
     const int per_cta = (int)((int64_t)a.n_reads * 3 / 4 / grid);
     a.steal_base = per_cta * grid;
+    static const int turn_batch = getenv("DARTGPU_TURN_BATCH") ? atoi(getenv("DARTGPU_TURN_BATCH")) : 6;
+    a.turn_batch = turn_batch;
     cudaMemsetAsync(a.steal, 0, sizeof(uint32_t), st);
     if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
     else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
