@@ -141,7 +141,7 @@ void build_index_files(int device, const uint8_t *pac, int64_t l_pac, const char
 struct SeedLaunch {
     const uint8_t *codes; const int64_t *dev_off; const int32_t *rlen; int n_reads;
     const uint2 *packed;                                        // 16 bases per entry: .x = 2-bit codes (base i at bits 2i), .y = "not ACGT" bits
-    uint32_t *steal; int steal_base; int turn_batch;                            // work-stealing counter for the tail of the search kernel
+    uint32_t *steal; int steal_base; int turn_batch, end_batch;                            // work-stealing counter for the tail of the search kernel
     int cap_rec; uint32_t max_dup; int max_gaps, max_intron;
     SearchRec *recs; uint32_t *nrec; uint32_t *nhits;          // search output
     int64_t *seed_off;                                          // n_reads+1, exclusive scan of nhits

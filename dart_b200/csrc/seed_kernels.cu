@@ -109,9 +109,9 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     // History (ncu, round 1): with the whole turn-around inline 14 of 32 lanes were active; batching all of it (start-table
     // gather included) cut the time by a quarter but left lanes waiting 60 % of the iterations, because after every
     // mismatch a read goes through several searches of only 2-4 steps.
-    enum { ST_STEP = 0, ST_JUMP = 1, ST_NEED = 2, ST_DONE = 3 };
+    enum { ST_STEP = 0, ST_JUMP = 1, ST_NEED = 2, ST_DONE = 3, ST_END = 4 };
     const char *ktab = reinterpret_cast<const char *>(ix.ktab);
-    const int TURN_BATCH = a.turn_batch;
+    const int TURN_BATCH = a.turn_batch, END_BATCH = a.end_batch;
     bool own = true, have_read = false;
     int st = ST_NEED;
     int r = 0, rl = 0, start = 0, p = 0, cw = -1;
@@ -146,9 +146,23 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
 
     for (;;) {
         const unsigned need_m = __ballot_sync(FULL, st == ST_NEED);
+        const unsigned end_m = __ballot_sync(FULL, st == ST_END);
         const unsigned act_m = __ballot_sync(FULL, st == ST_STEP || st == ST_JUMP);
-        if ((need_m | act_m) == 0) break;
-        if (st == ST_NEED && (__popc(need_m) >= TURN_BATCH || act_m == 0)) {
+        if ((need_m | act_m | end_m) == 0) break;
+        // a finished segment: record it, advance (register arithmetic, but ~130 instructions: a few lanes share it)
+        if (st == ST_END && (__popc(end_m) >= END_BATCH || act_m == 0)) {       // bwt_search.cpp:173 and IdentifySeedPairs' advance
+            const int len = p - start;
+            if (x2 <= a.max_dup && len >= 16) {
+                if ((int)nr < a.cap_rec) {
+                    SearchRec rec; rec.sa_begin = x1; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
+                    a.recs[(int64_t)r * a.cap_rec + nr] = rec;
+                }
+                nr++; nh += x2;
+                start += len;
+            } else start++;
+            advance();
+        }
+        if (st == ST_NEED && (__popc(need_m) >= TURN_BATCH || (act_m | end_m) == 0)) {
             if (have_read) { a.nrec[r] = nr; a.nhits[r] = nh; have_read = false; }
             if (own) { r = atomicAdd(&s_next, 1); if (r >= r_end) own = false; }
             if (!own) r = a.steal_base + (int)atomicAdd(a.steal, 1u);
@@ -208,18 +222,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                     st = ST_STEP;
                 }
             }
-            if (end) {                                   // bwt_search.cpp:173 and IdentifySeedPairs' advance
-                const int len = p - start;
-                if (x2 <= a.max_dup && len >= 16) {
-                    if ((int)nr < a.cap_rec) {
-                        SearchRec rec; rec.sa_begin = x1; rec.freq = x2; rec.start = (uint16_t)start; rec.len = (uint16_t)len;
-                        a.recs[(int64_t)r * a.cap_rec + nr] = rec;
-                    }
-                    nr++; nh += x2;
-                    start += len;
-                } else start++;
-                advance();
-            }
+            if (end) st = ST_END;
         }
     }
     if (have_read) { a.nrec[r] = nr; a.nhits[r] = nh; }
@@ -254,6 +257,8 @@ void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
     a.steal_base = per_cta * grid;
     static const int turn_batch = getenv("DARTGPU_TURN_BATCH") ? atoi(getenv("DARTGPU_TURN_BATCH")) : 6;
     a.turn_batch = turn_batch;
+    static const int end_batch = getenv("DARTGPU_END_BATCH") ? atoi(getenv("DARTGPU_END_BATCH")) : 4;
+    a.end_batch = end_batch;
     cudaMemsetAsync(a.steal, 0, sizeof(uint32_t), st);
     if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
     else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
