@@ -6,16 +6,15 @@
 // (IdentifySeedPairs, GenerateAlignmentCandidate).
 //
 // Execution model
-//   * ONE THREAD owns one FM chain.  A rank query is one 128-bit load (the two bit-planes of 64 symbols) plus one 32-bit
-//     load (the count of the wanted symbol) from a single 32-byte sector (Occ32, rank.cuh), one masked popcount and no
-//     cross-lane traffic.  Round-1 history: the first kernels ranked a 64-byte block with 4 cooperating lanes
+//   * ONE THREAD owns one FM chain.  A rank query is one 256-bit load of a single 32-byte sector (Occ32, rank.cuh: the
+//     four counts and the two bit-planes of 64 symbols), one masked popcount and no cross-lane traffic.  Round-1 history: the first kernels ranked a 64-byte block with 4 cooperating lanes
 //     (4 x 128-bit loads, popcounts combined with shuffles); ncu showed them bound by the integer pipes (~100
 //     instructions per LANE per step, i.e. ~400 thread-instructions per step) with the 4.6 MB table L2-resident, and by
 //     too few independent chains in flight once the table lives in HBM.  Thread-per-chain needs ~6x fewer
 //     thread-instructions per step, puts 4x more chains in flight per SM and touches half the bytes per query.
 //   * the nested loops of the reference (reads > search starts > extension steps) are flattened into a single loop whose
-//     every iteration performs exactly one rank step, so the 32 lanes of a warp stay converged although their reads,
-//     search starts and match lengths differ; a lane draws its next read the moment it finishes one.
+//     every iteration issues one 256-bit load per lane — a rank step or a search-start table lookup — so the 32 lanes of
+//     a warp stay converged although their reads, search starts and match lengths differ (states in k_search).
 //   * reads arrive 2-bit packed (+1 bit "not ACGT"), 16 bases per 8-byte entry, written by k_encode_reads.
 //   * search only records SA intervals (of the reverse-complemented pattern, see k_search); after a prefix sum over
 //     the hit counts a second kernel resolves every hit with its own thread (LF walk to the next kept SA entry — none at
