@@ -162,7 +162,7 @@ void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, 
 // nw_kernel.cu
 struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int64_t aux_off; int32_t m, n; };
 struct NwScratch {         // sort buffers of the thread-per-job NW class, owned by the context
-    DevBuf<uint32_t> keys, vals, keys2, vals2;
+    DevBuf<uint32_t> keys, vals, keys2, vals2, counter;
     DevBuf<uint8_t> tmp;
 };
 constexpr int NW_LAUNCHES = 4;     // sort keys, radix sort (counted once), k_nw_thread, k_nw

@@ -182,12 +182,22 @@ __global__ void k_nw_sort_keys(const NwJobDev *__restrict__ jobs, int n_jobs, ui
 
 __global__ void __launch_bounds__(NWT_THREADS)
 k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, const uint32_t *__restrict__ order,
-            const uint32_t *__restrict__ sorted_keys, int n_jobs, uint32_t *flags, uint8_t *ops, int32_t *nops)
+            const uint32_t *__restrict__ sorted_keys, int n_jobs, uint32_t *next_chunk, uint32_t *flags, uint8_t *ops, int32_t *nops)
 {
     __shared__ int16_t sS[NWT_MAX + 1][NWT_THREADS], sT[NWT_MAX + 1][NWT_THREADS];
     const int tid = threadIdx.x;
-    for (int k0 = blockIdx.x * NWT_THREADS; k0 < n_jobs; k0 += gridDim.x * NWT_THREADS) {
-        const int k = k0 + tid;
+    __shared__ int s_chunk;
+    const int n_chunks = (n_jobs + NWT_THREADS - 1) / NWT_THREADS;
+    // chunks of 128 shape-sorted jobs are handed out dynamically, the largest shapes first, so that the CTAs finish together
+    // (with a static stride the CTAs that drew the chunks of 60 x 60 jobs ran long after the others: the bench's 250 k-job
+    // launches took 3x longer per job than a 1 M-job launch)
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_chunk = (int)atomicAdd(next_chunk, 1u);
+        __syncthreads();
+        const int chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int k = (n_chunks - 1 - chunk) * NWT_THREADS + tid;
         if (k >= n_jobs || sorted_keys[k] == 0xFFFFu) continue;       // sorted: warp-class jobs are at the end
         const int job = (int)order[k];
         const NwJobDev J = jobs[job];
@@ -299,7 +309,9 @@ void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, i
     tmp = S.tmp.cap;
     cub::DeviceRadixSort::SortPairs(S.tmp.p, tmp, S.keys.p, S.keys2.p, S.vals.p, S.vals2.p, n_jobs, 0, 16, st);
     int gt = (n_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > 148 * 6) gt = 148 * 6;
-    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, jobs, S.vals2.p, S.keys2.p, n_jobs, flags, ops, nops);
+    S.counter.reserve(4);
+    cudaMemsetAsync(S.counter.p, 0, sizeof(uint32_t), st);
+    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, jobs, S.vals2.p, S.keys2.p, n_jobs, S.counter.p, flags, ops, nops);
     // everything larger: a warp per job
     int want = (n_jobs + (NW_THREADS / 32) - 1) / (NW_THREADS / 32);
     int grid = want < 148 * 8 ? want : 148 * 8;
