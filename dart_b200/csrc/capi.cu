@@ -172,7 +172,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[3], st));
     launch_scan_hits(a, c->d_scan_tmp.p, tmp, st);
-    DG_CUDA(cudaMemcpyAsync(c->h_total.p, c->d_seed_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(c->h_total.p, c->d_seed_off.p + n, sizeof(int64_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int64_t total = c->h_total.p[0];
     c->total_seeds = total;
@@ -210,7 +210,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
         }
         c->stats.d2h_bytes += (n + 1) * 8 + n * 4 + total * 20;
     }
-    DG_CUDA(cudaMemcpyAsync(c->h_dstats.p, c->d_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    small_d2h(c->h_dstats.p, c->d_stats.p, sizeof(DevStats), st);
     DG_CUDA(cudaEventRecord(c->ev[7], st));
     DG_CUDA(dg_stream_sync(st));
     add_ms(c, &c->stats.ms_h2d, c->ev[0], c->ev[1]);

@@ -126,6 +126,7 @@ inline cudaError_t dg_stream_sync(cudaStream_t st)
 // kernel launchers (each file owns its kernels; all work is enqueued on `st`)
 // ---------------------------------------------------------------------------------------------------
 // index_device.cu
+void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t st);   // bytes: multiple of 4, pinned destination
 void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *occ, uint64_t n_blocks32, cudaStream_t st);
 // sa_file: the reference's sampled SA (every sa_intv-th entry, entry 0 = -1) on the device; out: every 2^shift-th entry
 void launch_build_ktab(const DevIndex &ix, int K, KmerStart *out, KmerStart *tmp, cudaStream_t st);   // out, tmp: 4^K entries each

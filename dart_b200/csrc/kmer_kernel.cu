@@ -407,7 +407,7 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
     k_kmer_prep<<<g1, 256, 0, st>>>(codes, jobs, n_jobs, tab_cap, cap_max, S.ntiles.p, S.cap.p, S.count.p, S.heavy_list.p, S.heavy_count.p, out);
     launch_scan_u32_to_i64(S.ntiles.p, S.tile_off.p, n_jobs, S.scan_tmp.p, tmp, st);
     launch_scan_u32_to_i64(S.cap.p, S.rec_off.p, n_jobs, S.scan_tmp.p, tmp, st);
-    DG_CUDA(cudaMemcpyAsync(S.h_total.p, S.rec_off.p + n_jobs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(S.h_total.p, S.rec_off.p + n_jobs, sizeof(int64_t), st);
     DG_CUDA(dg_stream_sync(st));
     S.recs.reserve((size_t)S.h_total.p[0] + 1);
     k_kmer_scan<<<148 * 8, KS_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, S.tile_off.p, S.rec_off.p, S.cap.p, S.count.p, S.recs.p);

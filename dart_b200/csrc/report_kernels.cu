@@ -6,6 +6,8 @@
 // Replaces GenMappingReport and its callers' per-read logic (/root/reference/src/AlignmentCandidates.cpp:1079-1207,
 // /root/reference/src/Mapping.cpp:600-621) — see report_logic.cuh for the line-by-line map.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 
 #include "context.h"
 #include "report_logic.cuh"
@@ -286,7 +288,7 @@ static void scan_u32(dartgpu_ctx *c, DevicePipe *D, const uint32_t *in, int64_t 
 
 static int64_t fetch_i64(dartgpu_ctx *c, DevicePipe *D, const int64_t *dev)
 {
-    DG_CUDA(cudaMemcpyAsync(D->h_vals.p, dev, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    small_d2h(D->h_vals.p, dev, sizeof(int64_t), c->stream);
     DG_CUDA(dg_stream_sync(c->stream));
     return D->h_vals.p[0];
 }
@@ -305,10 +307,10 @@ static void nw_round(dartgpu_ctx *c, DevicePipe *D, NwJobDev *jobs, int nj, bool
     scan_u32(c, D, D->u32_c.p, D->scan_c.p, nj);
     DG_CUDA(cudaMemsetAsync(D->counters.p + 4, 0, 2 * sizeof(int32_t), st));
     k_nw_offsets<<<grid_for(nj), TPB, 0, st>>>(jobs, nj, D->scan_a.p, D->scan_b.p, D->scan_c.p, D->counters.p + 4, D->counters.p + 5, D->work.p);
-    DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 0, D->scan_a.p + nj, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 1, D->scan_b.p + nj, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 2, D->scan_c.p + nj, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(D->h_vals.p + 0, D->scan_a.p + nj, 8, st);
+    small_d2h(D->h_vals.p + 1, D->scan_b.p + nj, 8, st);
+    small_d2h(D->h_vals.p + 2, D->scan_c.p + nj, 8, st);
+    small_d2h(D->h_counters.p, D->counters.p + 4, 2 * sizeof(int32_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int64_t ops_total = D->h_vals.p[0], flag_total = D->h_vals.p[1], aux_total = D->h_vals.p[2];
     const int max_n = D->h_counters.p[0];
@@ -384,7 +386,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     // ---- phase A -> 8-mer re-seeding ----
     k_phase<0><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
-    DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(D->h_counters.p, D->counters.p, sizeof(int32_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int nk = D->h_counters.p[0];
     if (nk > 0) {
@@ -403,7 +405,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     E.njobs = D->jobsB.p; E.njob_count = D->counters.p + 1;
     k_phase<1><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
-    DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(D->h_counters.p, D->counters.p + 1, sizeof(int32_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int nB = D->h_counters.p[0];
     nw_round(c, D, D->jobsB.p, nB, true, D->opsB, D->nopsB);
@@ -413,7 +415,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     E.njobs = D->jobsC.p; E.njob_count = D->counters.p + 2;
     k_phase<2><<<grid_for(ncand), TPB, 0, st>>>(E, ncand);
     DG_CUDA(cudaGetLastError());
-    DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(D->h_counters.p, D->counters.p + 2, sizeof(int32_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int nC = D->h_counters.p[0];
     nw_round(c, D, D->jobsC.p, nC, false, D->opsC, D->nopsC);
@@ -442,9 +444,9 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     DG_CUDA(cudaGetLastError());
     scan_u32(c, D, D->text_len.p, D->text_off.p, nrep);
     scan_u32(c, D, D->njunc.p, D->junc_off.p, n);
-    DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 0, D->text_off.p + nrep, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(D->h_vals.p + 1, D->junc_off.p + n, 8, cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(D->h_counters.p, D->counters.p + 6, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    small_d2h(D->h_vals.p + 0, D->text_off.p + nrep, 8, st);
+    small_d2h(D->h_vals.p + 1, D->junc_off.p + n, 8, st);
+    small_d2h(D->h_counters.p, D->counters.p + 6, sizeof(int32_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int64_t text_total = D->h_vals.p[0], junc_total = D->h_vals.p[1];
     if (D->h_counters.p[0]) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("CIGAR pool capacity exceeded"));
@@ -457,15 +459,23 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     // ---- only the final records cross PCIe ----
     D->h_rr.reserve(n + 1); D->h_rep.reserve(nrep + 1); D->h_text.reserve(text_total + 1); D->h_junc.reserve(junc_total + 1);
     static const bool skip_d2h = getenv("DARTGPU_EXPERIMENT_SKIP_D2H") != nullptr;   // timing experiment only: results stay on the device
+    static const bool trace = getenv("DARTGPU_TRACE") != nullptr;
+    const double t_enq = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0;
+    if (trace) DG_CUDA(dg_stream_sync(st));
+    const double t_cmp = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0;
     if (!skip_d2h) {
     DG_CUDA(cudaMemcpyAsync(D->h_rr.p, D->rr.p, (size_t)n * sizeof(dartgpu_read_result), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_rep.p, D->rep.p, (size_t)nrep * sizeof(dartgpu_report), cudaMemcpyDeviceToHost, st));
     }
     if (text_total) DG_CUDA(cudaMemcpyAsync(D->h_text.p, D->text.p, text_total, cudaMemcpyDeviceToHost, st));
     if (junc_total) DG_CUDA(cudaMemcpyAsync(D->h_junc.p, D->junc.p, (size_t)junc_total * sizeof(dartgpu_junction), cudaMemcpyDeviceToHost, st));
-    DG_CUDA(cudaMemcpyAsync(D->h_work.p, D->work.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    small_d2h(D->h_work.p, D->work.p, 4 * sizeof(unsigned long long), st);
     DG_CUDA(cudaEventRecord(c->ev[14], st));
     DG_CUDA(dg_stream_sync(st));
+    if (trace) {
+        const double t_done = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        fprintf(stderr, "TRACE ctx %p enq %.3f compute_done %.3f d2h_done %.3f\n", (void *)c, t_enq, t_cmp, t_done);
+    }
     c->stats.nw_cells += D->h_work.p[0]; c->stats.kmer_window_bases += D->h_work.p[1]; c->stats.kmer_read_bases += D->h_work.p[2];
     add_ms(c, &c->stats.ms_report, c->ev[12], c->ev[13]);
     add_ms(c, &c->stats.ms_d2h, c->ev[13], c->ev[14]);
