@@ -458,15 +458,12 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
 
     // ---- only the final records cross PCIe ----
     D->h_rr.reserve(n + 1); D->h_rep.reserve(nrep + 1); D->h_text.reserve(text_total + 1); D->h_junc.reserve(junc_total + 1);
-    static const bool skip_d2h = getenv("DARTGPU_EXPERIMENT_SKIP_D2H") != nullptr;   // timing experiment only: results stay on the device
-    static const bool trace = getenv("DARTGPU_TRACE") != nullptr;
+    static const bool trace = getenv("DARTGPU_TRACE") != nullptr;   // host timeline of the compute / result-copy phases (adds a sync)
     const double t_enq = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0;
     if (trace) DG_CUDA(dg_stream_sync(st));
     const double t_cmp = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0;
-    if (!skip_d2h) {
     DG_CUDA(cudaMemcpyAsync(D->h_rr.p, D->rr.p, (size_t)n * sizeof(dartgpu_read_result), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(D->h_rep.p, D->rep.p, (size_t)nrep * sizeof(dartgpu_report), cudaMemcpyDeviceToHost, st));
-    }
     if (text_total) DG_CUDA(cudaMemcpyAsync(D->h_text.p, D->text.p, text_total, cudaMemcpyDeviceToHost, st));
     if (junc_total) DG_CUDA(cudaMemcpyAsync(D->h_junc.p, D->junc.p, (size_t)junc_total * sizeof(dartgpu_junction), cudaMemcpyDeviceToHost, st));
     small_d2h(D->h_work.p, D->work.p, 4 * sizeof(unsigned long long), st);
