@@ -65,10 +65,10 @@ class Stats(C.Structure):
 KMER_JOB = np.dtype([("frag_off", "<i8"), ("frag_len", "<i4"), ("glen", "<i4"), ("gpos", "<i8")])
 KMER_HIT = np.dtype([("rpos", "<i4"), ("gpos", "<i4"), ("len", "<i4")])
 NW_JOB = np.dtype([("frag_off", "<i8"), ("m", "<i4"), ("n", "<i4"), ("gpos", "<i8")])
-READ_RESULT = np.dtype([("mapq", "<i4"), ("score", "<i4"), ("sub_score", "<i4"), ("mis_num", "<i4"),
-                        ("n_reports", "<i4"), ("best", "<i4"), ("report_off", "<i8")])
-REPORT = np.dtype([("aln_score", "<i4"), ("sj_type", "<i4"), ("flag", "<i4"), ("paired_idx", "<i4"), ("dir", "<i4"),
-                   ("chr_idx", "<i4"), ("pos", "<i8"), ("cigar_off", "<i8"), ("cigar_len", "<i4"), ("reserved", "<i4")])
+READ_RESULT = np.dtype([("report_off", "<i8"), ("n_reports", "<i4"), ("best", "<i4"), ("score", "<i2"), ("sub_score", "<i2"),
+                        ("mis_num", "<i2"), ("mapq", "u1"), ("reserved", "u1")])
+REPORT = np.dtype([("pos", "<i8"), ("cigar_off", "<i4"), ("flag", "<i4"), ("paired_idx", "<i4"), ("chr_idx", "<i4"),
+                   ("aln_score", "<i2"), ("cigar_len", "<i2"), ("sj_type", "i1"), ("dir", "u1"), ("reserved", "u1", (2,))])
 JUNCTION = np.dtype([("g1", "<i8"), ("g2", "<i8"), ("type", "<i4"), ("read", "<i4")])
 
 # every symbol include/dartgpu.h declares (tests check the library exports all of them)

@@ -198,8 +198,8 @@ __global__ void k_read_final(Env E, int n_units, int paired, const int64_t *cand
         for (int m = 0; m < nr; m++) {
             int r = paired ? 2 * u + m : u;
             dartgpu_read_result o;
-            o.mapq = ro[m].mapq; o.score = ro[m].score; o.sub_score = ro[m].sub_score; o.mis_num = ro[m].mis_num;
-            o.n_reports = ro[m].n_reports; o.best = ro[m].best; o.report_off = rep_off[r];
+            o.mapq = (uint8_t)ro[m].mapq; o.score = (int16_t)ro[m].score; o.sub_score = (int16_t)ro[m].sub_score; o.mis_num = (int16_t)ro[m].mis_num;
+            o.n_reports = ro[m].n_reports; o.best = ro[m].best; o.report_off = rep_off[r]; o.reserved = 0;
             rr[r] = o;
             const int nc = (int)(cand_off[r + 1] - cand_off[r]);
             for (int k = 0; k < ro[m].n_reports; k++) {
@@ -210,7 +210,7 @@ __global__ void k_read_final(Env E, int n_units, int paired, const int64_t *cand
                     if (c.live && !c.skip && c.AlnScore > 0) tl = c.text_len;
                 }
                 text_len[rep_off[r] + k] = (uint32_t)tl;
-                rep[rep_off[r] + k].cigar_len = tl;
+                rep[rep_off[r] + k].cigar_len = (int16_t)tl;
             }
             njunc[r] = (uint32_t)emit_junctions(E, ro[m], E.cs + cand_off[r], nc, r, nullptr);
         }
@@ -226,7 +226,7 @@ __global__ void k_write_records(Env E, int n_reads, const int64_t *cand_off, con
         const int nc = (int)(cand_off[r + 1] - cand_off[r]);
         for (int k = 0; k < o.n_reports; k++) {
             dartgpu_report &p = rep[o.report_off + k];
-            p.cigar_off = text_off[o.report_off + k];
+            p.cigar_off = (int32_t)text_off[o.report_off + k];
             if (p.cigar_len > 0 && k < nc) {
                 const CandState &c = E.cs[cand_off[r] + k];
                 write_cigar_text(E.cig + c.cig_off, c.cig_n, text + p.cigar_off);
@@ -449,6 +449,7 @@ void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out)
     small_d2h(D->h_counters.p, D->counters.p + 6, sizeof(int32_t), st);
     DG_CUDA(dg_stream_sync(st));
     const int64_t text_total = D->h_vals.p[0], junc_total = D->h_vals.p[1];
+    if (text_total >= (1ll << 31)) throw std::make_pair(DARTGPU_ERR_ARG, std::string("batch too large: CIGAR text exceeds 2 GB, split the batch"));
     if (D->h_counters.p[0]) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("CIGAR pool capacity exceeded"));
     D->text.reserve(text_total + 1); D->junc.reserve(junc_total + 1);
     k_write_records<<<grid_for(n), TPB, 0, st>>>(E, n, D->cand_off.p, D->rr.p, D->rep.p, D->text_off.p, D->text.p, D->junc_off.p, D->junc.p);

@@ -789,20 +789,20 @@ HDN void read_best(const CandState *cs, int ncand, dartgpu_report *rep, ReadOut 
     r.n_reports = ncand > 0 ? ncand : 1;
     if (ncand == 0) {
         rep[0].aln_score = 0; rep[0].sj_type = -1; rep[0].flag = 0; rep[0].paired_idx = -1; rep[0].dir = 0; rep[0].chr_idx = 0;
-        rep[0].pos = 0; rep[0].cigar_off = 0; rep[0].cigar_len = 0; rep[0].reserved = 0;
+        rep[0].pos = 0; rep[0].cigar_off = 0; rep[0].cigar_len = 0; rep[0].reserved[0] = rep[0].reserved[1] = 0;
         return;
     }
     for (int k = 0; k < ncand; k++) {
         const CandState &a = cs[k];
         dartgpu_report &p = rep[k];
         p.aln_score = 0; p.sj_type = -1; p.flag = 0; p.paired_idx = a.PairedIdx; p.dir = 0; p.chr_idx = 0; p.pos = 0;
-        p.cigar_off = 0; p.cigar_len = 0; p.reserved = 0;
+        p.cigar_off = 0; p.cigar_len = 0; p.reserved[0] = p.reserved[1] = 0;
         if (!a.live) continue;
         p.sj_type = a.SJtype;
         if (a.skip) continue;
         p.aln_score = a.AlnScore;
         if (a.AlnScore > 0) {
-            p.dir = a.dir; p.chr_idx = a.chr; p.pos = a.pos; p.cigar_len = a.text_len;
+            p.dir = a.dir; p.chr_idx = a.chr; p.pos = a.pos; p.cigar_len = (int16_t)a.text_len;
             if (a.AlnScore > r.score) { r.best = k; r.mis_num = a.mis; r.sub_score = r.score; r.score = a.AlnScore; }
             else if (a.AlnScore == r.score) r.sub_score = r.score;
         }

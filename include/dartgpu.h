@@ -149,24 +149,28 @@ int dartgpu_nw_align(dartgpu_ctx *ctx, const char *bases, int64_t n_bases,
  * Set*AlignmentFlag, EvaluateMAPQ and the junctions UpdateLocalSJMap would record.  The caller keeps its own
  * reader and its own OutputPaired/SingledAlignments + OutputSpliceJunctions.
  * With params.pair_end the batch holds mates at 2i, 2i+1 (n_reads even). */
-typedef struct {            /* = the report fields of ReadItem_t (src/structure.h:156-163) */
-    int32_t mapq, score, sub_score, mis_num;
+/* The two result records are what crosses PCIe for every read (56 bytes per read with one report, 80 before): the fields are the
+ * reference's, the types as narrow as their ranges allow (scores and lengths are bounded by DARTGPU_MAX_RLEN). */
+typedef struct {            /* = the report fields of ReadItem_t (src/structure.h:156-163); 24 bytes */
+    int64_t report_off;     /* first AlignmentReport of this read in reports[] */
     int32_t n_reports;      /* CanNum */
     int32_t best;           /* iBestAlnCanIdx */
-    int64_t report_off;     /* first AlignmentReport of this read in reports[] */
+    int16_t score, sub_score, mis_num;
+    uint8_t mapq;
+    uint8_t reserved;
 } dartgpu_read_result;
 
-typedef struct {            /* = AlignmentReport_t + Coordinate_t (src/structure.h:117-141) */
-    int32_t aln_score;      /* AlnScore */
-    int32_t sj_type;        /* SJtype, -1 = none */
+typedef struct {            /* = AlignmentReport_t + Coordinate_t (src/structure.h:117-141); 32 bytes */
+    int64_t pos;            /* coor.gPos (1-based on the chromosome) */
+    int32_t cigar_off;      /* coor.CIGAR = cigars[cigar_off .. cigar_off+cigar_len) */
     int32_t flag;           /* iFrag (SAM FLAG); meaningful where the reference assigns it */
     int32_t paired_idx;     /* PairedAlnCanIdx */
-    int32_t dir;            /* coor.bDir (1 forward); valid when aln_score > 0 */
     int32_t chr_idx;        /* coor.ChromosomeIdx */
-    int64_t pos;            /* coor.gPos (1-based on the chromosome) */
-    int64_t cigar_off;      /* coor.CIGAR = cigars[cigar_off .. cigar_off+cigar_len) */
-    int32_t cigar_len;
-    int32_t reserved;
+    int16_t aln_score;      /* AlnScore */
+    int16_t cigar_len;
+    int8_t  sj_type;        /* SJtype, -1 = none */
+    uint8_t dir;            /* coor.bDir (1 forward); valid when aln_score > 0 */
+    uint8_t reserved[2];
 } dartgpu_report;
 
 typedef struct {            /* one UpdateLocalSJMap increment (src/Mapping.cpp:532-565) */

@@ -184,7 +184,7 @@ int main(int argc, char **argv)
         for (int k = 0; k < nc; k++) {
             const CandState &c = cs[cand_off[i] + k];
             dartgpu_report &p = rep[rr[i].report_off + k];
-            p.cigar_off = (int64_t)text.size();
+            p.cigar_off = (int32_t)text.size();
             if (c.live && !c.skip && c.AlnScore > 0) {
                 size_t at = text.size(); text.resize(at + c.text_len);
                 write_cigar_text(cig.data() + c.cig_off, c.cig_n, text.data() + at);

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
 def test_structs_match_the_header_layout():
     assert C.sizeof(capi.Params) == 40
     assert capi.KMER_JOB.itemsize == 24 and capi.NW_JOB.itemsize == 24 and capi.KMER_HIT.itemsize == 12
-    assert capi.READ_RESULT.itemsize == 32 and capi.REPORT.itemsize == 48 and capi.JUNCTION.itemsize == 24
+    assert capi.READ_RESULT.itemsize == 24 and capi.REPORT.itemsize == 32 and capi.JUNCTION.itemsize == 24
 
 
 def test_default_params_are_the_reference_defaults():
