@@ -186,18 +186,16 @@ k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__re
 {
     __shared__ int16_t sS[NWT_MAX + 1][NWT_THREADS], sT[NWT_MAX + 1][NWT_THREADS];
     const int tid = threadIdx.x;
-    __shared__ int s_chunk;
-    const int n_chunks = (n_jobs + NWT_THREADS - 1) / NWT_THREADS;
-    // chunks of 128 shape-sorted jobs are handed out dynamically, the largest shapes first, so that the CTAs finish together
-    // (with a static stride the CTAs that drew the chunks of 60 x 60 jobs ran long after the others: the bench's 250 k-job
-    // launches took 3x longer per job than a 1 M-job launch)
+    const int n_chunks = (n_jobs + 31) / 32;
+    // chunks of 32 shape-sorted jobs are handed out dynamically to the WARPS, the largest shapes first, so that the grid
+    // finishes together (with a static stride the CTAs that drew the chunks of 60 x 60 jobs ran long after the others on
+    // the bench's 250 k-job launches; a hand-out per CTA with a barrier made the warps of a CTA wait for each other)
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_chunk = (int)atomicAdd(next_chunk, 1u);
-        __syncthreads();
-        const int chunk = s_chunk;
+        int chunk = 0;
+        if ((tid & 31) == 0) chunk = (int)atomicAdd(next_chunk, 1u);
+        chunk = __shfl_sync(FULLM, chunk, 0);
         if (chunk >= n_chunks) break;
-        const int k = (n_chunks - 1 - chunk) * NWT_THREADS + tid;
+        const int k = (n_chunks - 1 - chunk) * 32 + (tid & 31);
         if (k >= n_jobs || sorted_keys[k] == 0xFFFFu) continue;       // sorted: warp-class jobs are at the end
         const int job = (int)order[k];
         const NwJobDev J = jobs[job];
