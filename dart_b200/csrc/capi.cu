@@ -343,7 +343,7 @@ static const uint8_t *upload_job_bases(dartgpu_ctx *c, const char *bases, int64_
 // ---------------------------------------------------------------------------------------------------
 SharedIndex::~SharedIndex() { cudaSetDevice(device); }   // the DevBuf members free on the right device
 
-// identity of an index for sharing: header fields + a hash of samples of the tables
+// identity of an index for sharing (device and SA density not included): header fields + a hash of samples of the tables
 static std::string index_key(int device, const dartgpu_index_view *v, int sa_shift, bool force64)
 {
     uint64_t h = 1469598103934665603ull;
@@ -356,7 +356,8 @@ static std::string index_key(int device, const dartgpu_index_view *v, int sa_shi
     for (int i = 0; i < v->n_seqs; i++) mix((uint64_t)v->seq_len_arr[i]);
     char buf[96];
     const char *kt = getenv("DARTGPU_KTAB");
-    snprintf(buf, sizeof buf, "%d:%016llx:%d:%d:%s", device, (unsigned long long)h, sa_shift, (int)force64, kt ? kt : "auto");
+    snprintf(buf, sizeof buf, "%016llx:%d:%s", (unsigned long long)h, (int)force64, kt ? kt : "auto");
+    (void)device; (void)sa_shift;
     return buf;
 }
 
@@ -392,13 +393,20 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
     }
 
     std::lock_guard<std::mutex> lock(g_index_mutex);
-    const std::string key = index_key(device, v, sa_shift, force64);
-    auto it = g_indexes.find(key);
-    if (it != g_indexes.end())
-        if (auto sp = it->second.lock()) return sp;
+    const std::string ident = index_key(device, v, sa_shift, force64);
+    const bool shift_pinned = getenv("DARTGPU_SA_SAMPLE") != nullptr;
+    std::shared_ptr<SharedIndex> peer;                       // the same index, resident on another GPU of this process
+    for (auto &kv : g_indexes) {
+        auto sp = kv.second.lock();
+        if (!sp || sp->ident != ident || (shift_pinned && sp->ix.sa_shift != sa_shift)) continue;
+        if (sp->device == device) return sp;                 // same device: share it
+        if (!peer) peer = sp;
+    }
+    if (peer) sa_shift = peer->ix.sa_shift;
+    const std::string key = std::to_string(device) + ":" + ident + ":" + std::to_string(sa_shift);
 
     auto S = std::make_shared<SharedIndex>();
-    S->device = device; S->key = key; S->G = v->l_pac;
+    S->device = device; S->key = key; S->ident = ident; S->G = v->l_pac;
     int64_t acc = 0;
     std::vector<std::pair<int64_t, int>> ends;
     for (int i = 0; i < v->n_seqs; i++) {
@@ -418,6 +426,29 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
     ix.primary = v->primary; ix.seq_len = v->seq_len;
     for (int i = 0; i < 5; i++) ix.L2[i] = v->L2[i];
     ix.G = S->G; ix.n_ends = (int)S->ends.size(); ix.force64 = force64;
+
+    if (peer) {
+        // Replicate GPU -> GPU (NVLink / NVSwitch: cudaMemcpyPeer) instead of a second host->device upload, re-layout and
+        // LF pass: for the 3.1 Gbp index that is ~31 GB over the switch instead of 5.4 GB over PCIe + 0.5 s of kernels.
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, device, peer->device);
+        if (can) { cudaError_t pe = cudaDeviceEnablePeerAccess(peer->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
+        const size_t sa_bytes = ((v->seq_len >> sa_shift) + 2) * sa_width;
+        const size_t kt_entries = peer->ix.ktab ? ((size_t)1 << (2 * peer->ix.ktab_k)) : 0;
+        S->d_occ32.reserve(occ_bytes); S->d_sa.reserve(sa_bytes); S->d_ref2.reserve(ref_words); S->d_ends.reserve(S->ends.size());
+        if (kt_entries) S->d_ktab.reserve(kt_entries);
+        DG_CUDA(cudaMemcpyPeerAsync(S->d_occ32.p, device, peer->d_occ32.p, peer->device, occ_bytes, st));
+        DG_CUDA(cudaMemcpyPeerAsync(S->d_sa.p, device, peer->d_sa.p, peer->device, sa_bytes, st));
+        DG_CUDA(cudaMemcpyPeerAsync(S->d_ref2.p, device, peer->d_ref2.p, peer->device, ref_words * 4, st));
+        DG_CUDA(cudaMemcpyPeerAsync(S->d_ends.p, device, peer->d_ends.p, peer->device, S->ends.size() * 8, st));
+        if (kt_entries) DG_CUDA(cudaMemcpyPeerAsync(S->d_ktab.p, device, peer->d_ktab.p, peer->device, kt_entries * sizeof(KmerStart), st));
+        DG_CUDA(dg_stream_sync(st));
+        ix.occ32 = reinterpret_cast<const Occ32 *>(S->d_occ32.p); ix.sa = S->d_sa.p;
+        ix.ktab = kt_entries ? S->d_ktab.p : nullptr; ix.ktab_k = peer->ix.ktab_k;
+        ix.ref2 = S->d_ref2.p; ix.chr_ends = S->d_ends.p;
+        g_indexes[key] = S;
+        return S;
+    }
 
     // Occ blocks: raw BWA words up, re-laid-out on the device
     const uint64_t n_blocks128 = (v->seq_len + 127) / 128;

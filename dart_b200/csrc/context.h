@@ -14,7 +14,7 @@ namespace dartgpu {
 // full suffix array instead of one per thread.
 struct SharedIndex {
     int device = 0;
-    std::string key;
+    std::string key, ident;
     DevIndex ix{};
     int64_t G = 0;
     std::vector<std::string> names;

@@ -57,6 +57,18 @@ def test_result_is_independent_of_batching_and_host_threads():
     _compare(gs, rs, gj, rj)
 
 
+def test_two_gpus_give_the_same_records():
+    """Reads shard over the GPUs of a box (contiguous ranges, no collective); the second GPU's index is replicated from the
+    first over NVLink (cudaMemcpyPeer) instead of a second upload.  Same records, same junctions."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w = workload("c3")
+    rs, rj = run_reference(w, "dart_canon", 1, ("-mis", "5"), tag="ref_mis5")
+    gs, gj = _run_gpu(w, ("-mis", "5"), tag="gpu_two_devices", more=("-devices", "0,1", "-batch", "700"))
+    _compare(gs, rs, gj, rj)
+
+
 def test_golden_sam():
     """The committed golden SAM (generated in the build container from the reference) — no oracle/_ref needed."""
     w = dict(dir=os.environ.get("DART_TEST_DIR", "/tmp/dart_b200_tests"), idx=GOLDEN + "/idx", flags=["-mis", "5"])
