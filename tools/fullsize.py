@@ -32,7 +32,6 @@ def write_pairs(g, cfg, n_pairs, r1, r2, chunk=500_000):
     """FASTQ files for n_pairs of the named config, generated in chunks (seeded per chunk)."""
     with open(r1, "wb") as f1, open(r2, "wb") as f2:
         done = 0
-        flat = None
         while done < n_pairs:
             k = min(chunk, n_pairs - done)
             seed = (2003 if cfg == 3 else 2004) * 1000 + done // chunk
@@ -44,7 +43,6 @@ def write_pairs(g, cfg, n_pairs, r1, r2, chunk=500_000):
             f1.write(synth.fastq_bytes(m1, 1, first_id=done))
             f2.write(synth.fastq_bytes(m2, 2, first_id=done))
             done += k
-    del flat
 
 
 def samhash(exe, sam, dump=None):
