@@ -416,10 +416,8 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
     // whatever the fast path declined: the ring kernel, reading the list's length on the device
     const int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
     const size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8 + 2048) * 4;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    if (smem > 48 * 1024) {          // the opt-in is per device and cheap: set it on the device this launch goes to
+        DG_CUDA(cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int grid = n_jobs < 148 * 4 ? n_jobs : 148 * 4;
     k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, S.heavy_list.p, S.heavy_count.p, tab_cap, ring, out);
