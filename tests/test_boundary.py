@@ -62,3 +62,24 @@ def test_index_build_rejects_bad_arguments():
     assert L.dartgpu_index_build(0, None, 100, b"/tmp/x", 0) == -4
     buf = (C.c_uint8 * 8)()
     assert L.dartgpu_index_build(0, buf, 0, b"/tmp/x", 0) == -4
+
+
+def test_samhash_is_order_independent(tmp_path):
+    """tools/samhash.cpp (the full-size parity check's fingerprint): header lines ignored, record order irrelevant,
+    any changed byte visible."""
+    import random
+    import subprocess
+    exe = str(tmp_path / "samhash")
+    subprocess.run(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tools", "samhash.cpp")], check=True)
+    lines = [l for l in open(os.path.join(GOLDEN, "pe.sam")) if not l.startswith("@")]
+    a, b, c = tmp_path / "a.sam", tmp_path / "b.sam", tmp_path / "c.sam"
+    a.write_text("@HD\tVN:1.0\n" + "".join(lines))
+    shuffled = lines[:]
+    random.Random(5).shuffle(shuffled)
+    b.write_text("@PG\tID:x\n@SQ\tSN:chr1\tLN:5\n" + "".join(shuffled))
+    changed = lines[:]
+    changed[17] = changed[17].replace("\t", "\tX", 1)
+    c.write_text("".join(changed))
+    h = lambda p: subprocess.run([exe, str(p)], check=True, capture_output=True, text=True).stdout.split()  # noqa: E731
+    assert h(a) == h(b) and h(a)[0] == str(len(lines))
+    assert h(c) != h(a)
