@@ -22,8 +22,6 @@ import sys
 import threading
 import time
 
-from concurrent.futures import ThreadPoolExecutor
-
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,6 +35,7 @@ MIS = os.environ.get("DART_BENCH_MIS")  # None = as BASELINE names the config (n
 # config[2] (multi-contig genome with gene models, spliced pairs; DART_BENCH_SCALE x 3.1 Gbp) whose Occ table no longer
 # fits L2 — used for the HBM-bound roofline of k_search in profiles/, never for the headline line.
 CONTEXTS = int(os.environ.get("DART_BENCH_CONTEXTS", 4))
+NW_OPS_PER_CELL = 22   # integer instructions of the recurrence + traceback flags per cell in k_nw_thread's inner loop (SASS listing in profiles/)
 WORKLOAD = os.environ.get("DART_BENCH_WORKLOAD", "c2")
 SCALE = float(os.environ.get("DART_BENCH_SCALE", "0.06"))
 
@@ -170,6 +169,23 @@ def run_reference_arm(args, rank):
     }))
 
 
+def hotpath_baseline(g, idx, cores):
+    """The reference's hot-path calls ONLY (IdentifySeedPairs ... EvaluateMAPQ, src/Mapping.cpp:600-639) over pre-parsed
+    reads on all host cores, through oracle/_ref/libdartref.so: no FASTQ parsing, no SAM text, no file IO — the like-for-like
+    denominator of `value` / `e2e` next to the stock binary's number."""
+    from oracle import pyoracle as po
+    sp = 100_000
+    m1, m2 = make_pairs(g, sp, 0)
+    b = as_batch(m1, m2)
+    R = po.Reference(idx)
+    R.set_params(max_mismatch=int(MIS) if MIS else 0, pair_end=1, **({"multi_hit": 1, "max_dup": 10000, "all_sj": 1} if WORKLOAD == "c5" else {}))
+    R.hotpath(b.bases, b.offsets, 1, cores)               # warm-up (page in the index)
+    sec = R.hotpath(b.bases, b.offsets, 1, cores)
+    return {"value": b.n / sec, "unit": "reads/s", "cores": cores, "kind": "reference",
+            "sample": f"{sp} pairs of the same workload, the reference's own per-read functions (libdartref.so) on {cores} threads, "
+                      "reads pre-parsed in memory, no output formatting"}
+
+
 def workload_config(sample_pairs=None):
     wl = ("BASELINE config[1]: synthetic 4.6 Mbp random genome (seed 1001), paired-end 2x101 bp, 1% substitutions, FR fragments ~N(300,30)"
           if WORKLOAD == "c2" else
@@ -181,6 +197,141 @@ def workload_config(sample_pairs=None):
             "sharding": "contiguous read range per GPU, index replicated per HBM, no collective",
             "l2": "read batch (226 MB of codes per GPU) is larger than L2; " + ("the 4.6 MB Occ table of this config is L2-resident by nature"
                                                                                  if WORKLOAD == "c2" else "the Occ table is larger than L2 (HBM gathers)")}
+
+
+class Lanes:
+    """K contexts of one GPU driven by ONE host thread: submit on each, then wait on each (dartgpu_submit / dartgpu_wait),
+    so K batches are in flight and the copies / kernels of consecutive batches overlap.  The thread sleeps in dartgpu_wait."""
+
+    def __init__(self, mappers, subs):
+        self.mappers, self.subs = mappers, subs
+
+    def upload(self):
+        for m, sb in zip(self.mappers, self.subs):
+            m.upload_reads(sb)
+
+    def run(self, resident, steps):
+        """`steps` passes over the batch, the sub-batches round-robin over the contexts; a context is only waited for when
+        its next batch is due (no barrier between steps: that would run the contexts in lockstep)."""
+        busy = [False] * len(self.mappers)
+        for _ in range(steps):
+            for i, (m, sb) in enumerate(zip(self.mappers, self.subs)):
+                if busy[i]:
+                    m.wait(copy=False)
+                m.submit(None if resident else sb)
+                busy[i] = True
+        for i, m in enumerate(self.mappers):
+            if busy[i]:
+                m.wait(copy=False)
+
+    def stats(self):
+        sts = [m.stats() for m in self.mappers]
+        return {k: sum(x[k] for x in sts) for k in sts[0]}
+
+
+def make_lanes(capi, idx, local, params, batch, contexts):
+    from dart_b200.shard import shard_bounds
+    mappers = [capi.Mapper(idx, device=local, **params) for _ in range(contexts)]
+    bounds = shard_bounds(batch.n, contexts, True)
+    subs = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        off = batch.offsets[a:b + 1]
+        subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]].copy(), (off - off[0]).copy()).pin())   # e2e: inputs in pinned host memory
+    return Lanes(mappers, subs)
+
+
+def search_roofline(M, batch, reps, peaks, l2_peak=None):
+    """Kernel-only seeding over the whole batch on one context (no host orchestration, no copies): roofline of k_search.
+    Algorithmic bytes = SURVEY.md 8d (64 B per BWA block the reference's steps touch + packed read + 16 B per record);
+    requested bytes = the 32-byte sectors the kernel really loads (device counter)."""
+    M.upload_reads(batch)
+    M.seed_resident()
+    ms = []
+    for _ in range(reps):
+        M.seed_resident()
+        ms.append(M.stats()["ms_search"])
+    sk = M.stats()
+    kms = float(np.mean(ms))
+    alg = 64 * sk["ext_blocks"] + (sk["read_bases"] + 3) // 4 + 16 * sk["seeds"]
+    req = 32 * sk["search_sector_loads"] + (sk["read_bases"] + 1) // 2 + 16 * sk["seeds"]   # packed read view: 8 B per 16 bases
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"kernel": "k_search (FM-index forward extension)", "kernel_ms": kms, "reads_in_launch": batch.n,
+           "algorithmic_bytes_per_launch": int(alg), "requested_bytes_per_launch": int(req),
+           "algorithmic_gbs": alg / (kms * 1e-3) / 1e9, "requested_gbs": req / (kms * 1e-3) / 1e9,
+           "hbm_peak_gbs": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+    if l2_peak:
+        out["l2_peak_gbs"] = l2_peak / 1e9
+    return out, sk
+
+
+def human_leg(args, rank, world, local, capi, barrier, allmax, peaks):
+    """BASELINE config[2] at FULL size (3.1 Gbp genome in 24 contigs with gene models, spliced pairs 2x101): the
+    HBM-bound case of the path, measured in the same run (extra keys of the bench line).  Index staged by the GPU builder
+    (byte-identical files, tests/test_index_build.py); untimed preparation."""
+    import psutil
+    from dart_b200 import synth
+    need = world * 14e9 + 8e9
+    if psutil.virtual_memory().available < need:
+        return {"skipped": f"host memory: {psutil.virtual_memory().available / 1e9:.0f} GB available, {need / 1e9:.0f} GB wanted for {world} ranks"}
+    t0 = time.perf_counter()
+    scale = float(os.environ.get("DART_BENCH_HUMAN_SCALE", "1.0"))
+    g = synth.config_genome(3, scale)
+    idx = os.path.join(WORK, f"idx_human_{scale}")
+    if rank == 0 and not all(os.path.exists(idx + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
+        capi.index_build(g, idx + ".tmp", device=local)
+        for e in (".bwt", ".sa", ".pac", ".ann", ".amb"):
+            os.replace(idx + ".tmp" + e, idx + e)
+    barrier()
+    pairs = int(os.environ.get("DART_BENCH_HUMAN_PAIRS", PAIRS_PER_GPU))
+    m1, m2 = synth.simulate_pairs(g, pairs, READ_LEN, 0.01, seed=2003 + rank, spliced=True, frag_min=202, frag_max=500)
+    batch = as_batch(m1, m2)
+    del g, m1, m2
+    params = dict(pair_end=1, host_threads=max(1, (os.cpu_count() or 1) // world))
+    lanes = make_lanes(capi, idx, local, params, batch, CONTEXTS)
+    prep_s = time.perf_counter() - t0
+    steps, warm = args.steps, max(3, args.warmup)
+    lanes.upload()
+    lanes.run(True, warm)
+    ms_res = allmax(timed_region(barrier, lambda: lanes.run(True, steps)))
+    st = lanes.stats()
+    lanes.run(False, 2)
+    ms_e2e = allmax(timed_region(barrier, lambda: lanes.run(False, steps)))
+    st_e2e = lanes.stats()
+    out = {"workload": f"BASELINE config[2] at x{scale} of full size: {int(3.1e9 * scale / 1e6)} Mbp genome in 24 contigs with gene models, "
+                       f"spliced pairs 2x101 bp, 1% substitutions; {pairs} pairs per GPU and step",
+           "value": world * batch.n * steps / (ms_res * 1e-3), "unit": "reads/s", "ms_per_step": ms_res / steps,
+           "e2e": {"value": world * batch.n * steps / (ms_e2e * 1e-3), "unit": "reads/s",
+                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
+           "n_gpus": world, "steps": steps, "warmup": warm, "prep_seconds_untimed": prep_s,
+           "kernels_ms_per_step": {k: st[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h")}}
+    if rank == 0:
+        M = lanes.mappers[0]
+        rf, sk = search_roofline(M, batch, max(3, steps), peaks)
+        ach, peak = rf["algorithmic_gbs"], rf["hbm_peak_gbs"]
+        traffic = None
+        try:   # DRAM bytes of the committed ncu capture of the same kernel on the same workload, scaled to this launch
+            t = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_ncu.json")))["config2_fullsize"]
+            traffic = int(t["dram_bytes_per_launch"] * batch.n / t["reads_in_launch"]) if scale == 1.0 else None
+        except Exception:
+            pass
+        out["roofline_hbm"] = {"bound": "hbm", "kernel": rf["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                               "traffic": traffic, "kernel_ms": rf["kernel_ms"], "algorithmic_bytes_per_launch": rf["algorithmic_bytes_per_launch"],
+                               "requested_bytes_per_launch": rf["requested_bytes_per_launch"], "peak_source": rf["peak_source"],
+                               "note": "3.1 GB Occ table + 1 GB start table: random sector gathers from HBM (L2 hit ~6 %)"}
+    for m in lanes.mappers:
+        m.close()
+    return out
+
+
+def timed_region(barrier, fn):
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
 
 
 def main():
@@ -196,19 +347,12 @@ def main():
         run_reference_arm(args, rank)
         return
 
-    # One host thread per context, and a thread that waits for its stream spins (lowest latency; measured at 2 GPUs: waiting
-    # on a blocking event instead costs 23 % of `value`).  So the contexts of all ranks together must not exceed the host's
-    # cores: 4 per GPU up to 4 GPUs on this 16-core box, 2 per GPU at 8.  Only if even one context per GPU does not fit
-    # do the threads wait asleep (DARTGPU_SYNC=block).
-    global CONTEXTS
-    cores_total = os.cpu_count() or 1
-    CONTEXTS = max(1, min(CONTEXTS, cores_total // world))
-    if world * CONTEXTS > cores_total:
-        os.environ.setdefault("DARTGPU_SYNC", "block")
+    # ONE host thread per GPU (this one) drives CONTEXTS contexts through dartgpu_submit / dartgpu_wait and sleeps while it
+    # waits: the number of batches in flight is no longer tied to the host's cores (round 1: one spinning thread per context,
+    # 32 spinners on a 32-core box at 8 GPUs, weak-scaling efficiency 0.58).
     import torch
     import torch.distributed as dist
     from dart_b200 import capi
-    from dart_b200.shard import shard_bounds
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -220,6 +364,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(ms):
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     if rank == 0:
         g, idx = prepare_genome()
     barrier()
@@ -230,92 +380,62 @@ def main():
         params["max_mismatch"] = int(MIS)
     if WORKLOAD == "c5":
         params.update(multi_hit=1, max_dup=10000, all_sj=1)
-    # CONTEXTS contexts (one host thread each, the C-ABI's unit of concurrency) share this GPU and split the step's batch:
-    # their H2D / kernels / D2H overlap on separate streams.  Host cores are divided among ranks and contexts.
     cores = os.cpu_count() or 1
-    params["host_threads"] = max(1, cores // (world * CONTEXTS))
-    mappers = [capi.Mapper(idx, device=local, **params) for _ in range(CONTEXTS)]
-    M = mappers[0]
+    params["host_threads"] = max(1, cores // world)      # OpenMP threads of the pageable-buffer staging only
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     batch = as_batch(*make_pairs(g, PAIRS_PER_GPU, rank))
     n_reads = batch.n
-    bounds = shard_bounds(n_reads, CONTEXTS, True)
-    subs = []
-    for a, b in zip(bounds[:-1], bounds[1:]):
-        off = batch.offsets[a:b + 1]
-        subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]].copy(), (off - off[0]).copy()).pin())   # e2e: inputs in pinned host memory
-    pool = ThreadPoolExecutor(CONTEXTS)
-
-    def run_steps(resident, steps):
-        """`steps` passes over the batch.  Every context maps its own slice `steps` times back to back; the contexts are
-        not re-synchronised between steps (a barrier per step would run them in lockstep: all in their kernels, then all
-        in their D2H, and nothing would overlap), only at the two ends of the timed region."""
-        def worker(m, sb):
-            for _ in range(steps):
-                m.map_reads(sb, resident, False)
-        futs = [pool.submit(worker, m, sb) for m, sb in zip(mappers, subs)]
-        for f in futs:
-            f.result()
-
-    def timed(resident, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_steps(resident, steps)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+    lanes = make_lanes(capi, idx, local, params, batch, CONTEXTS)
+    M = lanes.mappers[0]
 
     # ---- device-resident arm ----
-    for m, sb in zip(mappers, subs):
-        m.upload_reads(sb)
-    run_steps(True, args.warmup)
+    lanes.upload()
+    lanes.run(True, args.warmup)
     sampler = ClockSampler(local); sampler.start()
-    ms_res = timed(True, args.steps)
-    sts = [m.stats() for m in mappers]
+    ms_res = allmax(timed_region(barrier, lambda: lanes.run(True, args.steps)))
+    st = lanes.stats()
     # ---- end-to-end arm (host buffers in, host results out) ----
-    run_steps(False, max(1, args.warmup // 2))
-    ms_e2e = timed(False, args.steps)
-    sts_e2e = [m.stats() for m in mappers]
+    lanes.run(False, max(1, args.warmup // 2))
+    ms_e2e = allmax(timed_region(barrier, lambda: lanes.run(False, args.steps)))
+    st_e2e = lanes.stats()
     clocks = sampler.result()
-    st = {k: sum(x[k] for x in sts) for k in sts[0]}          # work and kernel time summed over the contexts of this rank
-    st_e2e = {k: sum(x[k] for x in sts_e2e) for k in sts_e2e[0]}
 
-    # one context alone on the GPU over the whole batch: per-kernel times without the other contexts' kernels in between
-    # (the per-step sums above are CUDA-event intervals on streams that share the device)
-    M.upload_reads(batch)
-    M.map_reads(batch, True, False)
-    M.map_reads(batch, True, False)
-    alone = M.stats()
-    int32_peak = M.int32_peak()
-    # kernel-only seeding over the whole batch on one context (no host orchestration, no copies): roofline of the dominant kernel
-    M.seed_resident()
-    ms_k = []
-    for _ in range(max(3, args.steps)):
-        M.seed_resident()
-        ms_k.append(M.stats()["ms_search"])
-    sk = M.stats()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        search_bytes = 64 * sk["ext_blocks"] + (sk["read_bases"] + 3) // 4 + 16 * sk["seeds"]
-        search_ms = float(np.mean(ms_k))
-        achieved = search_bytes / (search_ms * 1e-3) / 1e9
-        traffic = None
-        try:   # DRAM bytes of the ncu capture, scaled from its launch (400 k reads) to this launch
-            t = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_ncu.json")))
-            key = {"c2": "config1", "c3": "config2_fullsize"}.get(WORKLOAD if WORKLOAD == "c2" or SCALE == 1.0 else "")
-            traffic = int(t[key]["dram_bytes_per_launch"] * n_reads / t[key]["reads_in_launch"]) if key in t else None
-        except Exception:
-            pass
+        # one context alone on the GPU over the whole batch: per-kernel times without the other contexts' kernels in between
+        # (the per-step sums above are CUDA-event intervals on streams that share the device)
+        M.upload_reads(batch)
+        M.map_reads(batch, True, False)
+        M.map_reads(batch, True, False)
+        alone = M.stats()
+        int32_peak = M.int32_peak()
+        l2_peak = M.l2_peak(16 << 20)
+        rf, sk = search_roofline(M, batch, max(3, args.steps), peaks, l2_peak)
+        l2_resident = WORKLOAD == "c2" or (WORKLOAD == "c5" and SCALE <= 2)
+        if l2_resident:
+            # config[1]'s 4.6 MB Occ table + 16 MB start table live in L2 (ncu: L2 hit 92 %, DRAM 3 % of peak): the roof of the
+            # kernel is the L2's random-sector gather rate, measured on this GPU by dartgpu_measure_l2_peak, against the
+            # bytes the kernel really requests (32 B per sector load, counted on the device)
+            ach, peak = rf["requested_gbs"], l2_peak / 1e9
+            roof = {"bound": "l2", "kernel": rf["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "dartgpu_measure_l2_peak: random 32-byte sector gathers over a 16 MB L2-resident table, all SMs, CUDA events (this run)",
+                    "requested_bytes_per_launch": rf["requested_bytes_per_launch"], "kernel_ms": rf["kernel_ms"],
+                    "reference_algorithmic": {"bytes_per_launch": rf["algorithmic_bytes_per_launch"], "gbs": rf["algorithmic_gbs"],
+                                              "frac_of_hbm_peak": rf["algorithmic_gbs"] / rf["hbm_peak_gbs"],
+                                              "note": "SURVEY 8d bytes (64 B per BWA block of the reference's steps, incl. the steps the start table skips); "
+                                                      "these bytes never reach HBM on this index, so this is not a roofline fraction"},
+                    "note": "index is L2-resident: bound = L2 sector-gather rate (and instruction issue), not HBM; the HBM-bound case is `human_scale.roofline_hbm`"}
+        else:
+            ach, peak = rf["algorithmic_gbs"], rf["hbm_peak_gbs"]
+            roof = {"bound": "hbm", "kernel": rf["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": rf["peak_source"], "algorithmic_bytes_per_launch": rf["algorithmic_bytes_per_launch"], "kernel_ms": rf["kernel_ms"],
+                    "requested_bytes_per_launch": rf["requested_bytes_per_launch"], "note": "Occ table larger than L2: sector gathers from HBM"}
         line = {
             "metric": "reads/sec mapped", "value": world * n_reads * args.steps / (ms_res * 1e-3), "unit": "reads/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
@@ -323,42 +443,53 @@ def main():
             "data": "synthetic", "config": workload_config(), "clocks": clocks,
             "e2e": {"value": world * n_reads * args.steps / (ms_e2e * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
-            "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS,
-            "host_sync": os.environ.get("DARTGPU_SYNC", "spin"), "host_cores": os.cpu_count(),
-            "roofline": {"bound": "hbm", "kernel": "k_search (FM-index forward extension)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes_per_launch": int(search_bytes), "kernel_ms": search_ms,
-                         "note": ("config[1]'s 4.6 MB Occ table is L2-resident, so this kernel is bound by the integer pipes / L2, "
-                                  "not HBM; the fraction is reported against the HBM copy peak as the contract asks") if WORKLOAD == "c2"
-                                 else "Occ table larger than L2: 64-byte gathers from HBM"},
+            "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS, "host_threads_per_gpu": 1,
+            "host_sync": os.environ.get("DARTGPU_SYNC", "block (one sleeping wait per batch)"), "host_cores": os.cpu_count(),
+            "roofline": roof,
             "kernels_ms_per_step": {k: st[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h", "ms_host")},
-            "work_per_step": {k: int(st[k]) for k in ("ext_steps", "ext_blocks", "lf_steps", "hits", "seeds", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases")},
+            "work_per_step": {k: int(st[k]) for k in ("ext_steps", "ext_blocks", "search_sector_loads", "lf_steps", "hits", "seeds", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases")},
             "kernels_ms_one_context_alone": {k: alone[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h")},
             "nw_gcups": (alone["nw_cells"] / (alone["ms_nw"] * 1e-3) / 1e9) if alone["ms_nw"] > 0 else None,
-            "seed_gbs": achieved,
+            "seed_gbs": rf["algorithmic_gbs"],
         }
         if line["nw_gcups"]:
-            ops_per_cell = 22    # adds, max and compares of the restated recurrence + traceback flags (nw_kernel.cu), per cell
+            ops_per_cell = NW_OPS_PER_CELL
             line["nw_roofline"] = {"bound": "int32", "achieved_gcups": line["nw_gcups"], "int32_ops_per_s_measured": int32_peak,
                                    "ops_per_cell": ops_per_cell, "peak_gcups": int32_peak / ops_per_cell / 1e9,
                                    "frac": line["nw_gcups"] * 1e9 * ops_per_cell / int32_peak,
-                                   "note": "whole NW stage of one context alone (shape sort + both kernels + tracebacks), cells = sum of m*n"}
+                                   "note": "whole NW stage of one context alone (shape-class sort + both kernels + tracebacks), cells = sum of m*n; "
+                                           "ops_per_cell from the SASS listing profiles/r02_nw_thread_sass.txt"}
+    for m in lanes.mappers:
+        m.close()
+    del lanes, batch
+    # ---- the HBM-bound configuration in the same run ----
+    human = None
+    if os.environ.get("DART_BENCH_HUMAN", "1") != "0" and WORKLOAD == "c2":
+        try:
+            human = human_leg(args, rank, world, local, capi, barrier, allmax, peaks)
+        except Exception as ex:   # reported, never a reason to lose the headline measurement
+            human = {"failed": repr(ex)}
+    if rank == 0:
+        if human is not None:
+            line["human_scale"] = human
+            if "roofline_hbm" in human:
+                line["roofline_hbm"] = human["roofline_hbm"]
         if world == 1:
             try:
-                cores = os.cpu_count() or 1
                 extra = (["-mis", MIS] if MIS else []) + (["-m", "-max_dup", "10000", "-all_sj"] if WORKLOAD == "c5" else [])
                 sp = min(REF_SAMPLE_PAIRS, 100_000 if WORKLOAD != "c4" else 40_000)
                 r1, r2, e1, e2 = reference_setup(g, idx, sp)
                 load = min(time_reference(idx, e1, e2, 2, cores, extra) for _ in range(2))
                 t = max(time_reference(idx, r1, r2, 2 * sp, cores, extra) - load, 1e-6)
                 line["cpu_baseline"] = {"value": 2 * sp / t, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                        "sample": f"{sp} pairs of the same workload, oracle/_ref/dart_ref -t {cores}, index-load time subtracted"}
+                                        "sample": f"{sp} pairs of the same workload, oracle/_ref/dart_ref -t {cores} (FASTQ parse + map + SAM text + write), index-load time subtracted"}
             except Exception as ex:  # the baseline is reported, never a reason to lose the measurement
                 line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+            try:
+                line["cpu_baseline_hotpath"] = hotpath_baseline(g, idx, cores)
+            except Exception as ex:
+                line["cpu_baseline_hotpath"] = {"value": None, "sample": f"failed: {ex}"}
         print(json.dumps(line))
-    for m in mappers:
-        m.close()
     if world > 1:
         dist.destroy_process_group()
 

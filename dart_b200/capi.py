@@ -56,7 +56,7 @@ class Stats(C.Structure):
                                            "ms_d2h", "ms_total_device", "ms_host", "ms_report")] +
                 [(n, C.c_uint64) for n in ("kernel_launches", "ext_steps", "ext_blocks", "lf_steps", "hits", "seeds",
                                            "read_bases", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases",
-                                           "kmer_read_bases", "h2d_bytes", "d2h_bytes")])
+                                           "kmer_read_bases", "h2d_bytes", "d2h_bytes", "search_sector_loads")])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -77,7 +77,8 @@ EXPORTS = ["dartgpu_default_params", "dartgpu_create", "dartgpu_create_from_file
            "dartgpu_sequence_name", "dartgpu_sequence_length", "dartgpu_set_stream", "dartgpu_seed_and_cluster",
            "dartgpu_kmer_reseed", "dartgpu_nw_align", "dartgpu_map_reads", "dartgpu_get_stats",
            "dartgpu_upload_reads", "dartgpu_seed_and_cluster_resident", "dartgpu_synchronize",
-           "dartgpu_map_reads_resident", "dartgpu_index_build", "dartgpu_measure_int32_peak"]
+           "dartgpu_map_reads_resident", "dartgpu_index_build", "dartgpu_measure_int32_peak", "dartgpu_measure_l2_peak",
+           "dartgpu_submit", "dartgpu_submit_resident", "dartgpu_wait"]
 
 
 def load_library() -> C.CDLL:
@@ -105,6 +106,11 @@ def load_library() -> C.CDLL:
     L.dartgpu_nw_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(_NwResult)]
     L.dartgpu_map_reads.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
     L.dartgpu_map_reads_resident.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
+    L.dartgpu_submit.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.dartgpu_submit_resident.argtypes = [C.c_void_p]
+    L.dartgpu_wait.argtypes = [C.c_void_p, C.POINTER(_MapResult)]
+    L.dartgpu_measure_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.dartgpu_measure_l2_peak.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
     L.dartgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.dartgpu_upload_reads.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.dartgpu_seed_and_cluster_resident.argtypes = [C.c_void_p]
@@ -213,6 +219,12 @@ class Mapper:
         self._check(self.L.dartgpu_measure_int32_peak(self.h, C.byref(v)))
         return float(v.value)
 
+    def l2_peak(self, table_bytes: int = 16 << 20) -> float:
+        """Measured bytes/s of random one-sector gathers from an L2-resident table (k_search's roof on a small index)."""
+        v = C.c_double(0)
+        self._check(self.L.dartgpu_measure_l2_peak(self.h, int(table_bytes), C.byref(v)))
+        return float(v.value)
+
     # ---- IdentifySeedPairs + GenerateAlignmentCandidate ----
     def identify_seed_pairs(self, reads: ReadBatch) -> dict:
         out = _Seeds()
@@ -258,10 +270,27 @@ class Mapper:
         return [ops[off[i]:off[i + 1]] for i in range(len(arr))]
 
     # ---- the per-read loop body of ReadMapping ----
+    def submit(self, reads: ReadBatch = None):
+        """Enqueue a batch and return at once (reads=None: the batch uploaded with upload_reads). One batch per context."""
+        if reads is None:
+            self._check(self.L.dartgpu_submit_resident(self.h))
+        else:
+            self._held = reads      # page-locked caller buffers are read by the DMA engine until wait()
+            self._check(self.L.dartgpu_submit(self.h, C.byref(reads._c())))
+
+    def wait(self, copy: bool = True) -> dict:
+        out = _MapResult()
+        self._check(self.L.dartgpu_wait(self.h, C.byref(out)))
+        return self._result(out, copy)
+
     def map_reads(self, reads: ReadBatch, resident: bool = False, copy: bool = True) -> dict:
         out = _MapResult()
         fn = self.L.dartgpu_map_reads_resident if resident else self.L.dartgpu_map_reads
         self._check(fn(self.h, C.byref(reads._c()), C.byref(out)))
+        return self._result(out, copy)
+
+    @staticmethod
+    def _result(out, copy):
         if not copy:  # views into context-owned memory, valid until the next call
             return dict(reads=_view(out.reads, READ_RESULT, out.n_reads), reports=_view(out.reports, REPORT, out.n_reports),
                         n_cigar_bytes=out.n_cigar_bytes, junctions=_view(out.junctions, JUNCTION, out.n_junctions))

@@ -63,7 +63,79 @@ template <class F> static int guarded(dartgpu_ctx *c, F &&f)
 void stats_begin(dartgpu_ctx *c)
 {
     c->stats = dartgpu_stats{};
-    DG_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(DevStats), c->stream));
+}
+
+// a fresh control block for the batch (or for its next attempt)
+static void ctl_begin(dartgpu_ctx *c)
+{
+    DG_CUDA(cudaMemsetAsync(c->d_ctl.p, 0, sizeof(BatchCtl), c->stream));
+}
+static void ctl_fetch(dartgpu_ctx *c)      // enqueue the read-back of the control block (a one-warp kernel, not the copy engine)
+{
+    static_assert(sizeof(BatchCtl) % 4 == 0, "BatchCtl is copied word by word");
+    small_d2h(c->h_ctl.p, c->d_ctl.p, sizeof(BatchCtl), c->stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pool capacities (see BatchCtl): first guess from the batch's size, growth from an aborted attempt's counts
+// ---------------------------------------------------------------------------------------------------
+static void caps_for_batch(dartgpu_ctx *c)
+{
+    Caps &K = c->caps;
+    const int64_t n = c->n_reads, L = std::max(c->max_rlen, 32);
+    // test hook: DARTGPU_CAP_SHRINK=<d> divides every first guess by d, so that small batches overflow and take the retry path
+    static const int64_t shrink = [] { const char *e = getenv("DARTGPU_CAP_SHRINK"); return e ? std::max<int64_t>(1, atoll(e)) : (int64_t)1; }();
+    auto atleast = [](int64_t &v, int64_t want) { want = std::max<int64_t>(want / shrink, 16); if (v < want) v = want; };
+    atleast(K.seeds, 3 * n + 4096);
+    atleast(K.cands, 2 * n + 4096);
+    atleast(K.pool, 6 * n + 4096);
+    atleast(K.krecs, n / 2 + 65536);
+    atleast(K.cig, 12 * n + 4096);
+    atleast(K.text, 8 * n + 4096);
+    atleast(K.junc, n / 4 + 4096);
+    atleast(K.nw_ops[0], n * L / 16 + 65536);
+    atleast(K.nw_ops[1], n * L / 8 + 65536);
+    atleast(K.nw_flags, n * L / 8 + 65536);
+    atleast(K.nw_aux, n * L / 32 + 65536);
+}
+
+// Grows whatever the aborted attempt is known to need (+25 %).  An attempt stops at the first pool that overflows, so the
+// pools behind it are scaled by the same factor: a batch ten times the expected seed count needs ten times the rest too.
+static void caps_grow(dartgpu_ctx *c, const BatchCtl &H)
+{
+    Caps &K = c->caps;
+    double f = 1.0;
+    auto need = [&](int64_t &cap, long long have) {
+        if (have > cap) { f = std::max(f, (double)have / (double)std::max<int64_t>(cap, 1)); cap = have + have / 4 + 4096; return true; }
+        return false;
+    };
+    const bool seeds = need(K.seeds, H.total_seeds);
+    const bool cands = need(K.cands, std::max(H.ncand, H.nrep - c->n_reads));
+    const bool pool = need(K.pool, H.pool_total);
+    const bool krecs = need(K.krecs, H.kmer_recs);
+    const bool nwb = need(K.nw_ops[0], (long long)H.nw_ops[0]);
+    const bool nwc = need(K.nw_ops[1], (long long)H.nw_ops[1]);
+    const bool nwf = need(K.nw_flags, (long long)std::max(H.nw_flags[0], H.nw_flags[1]));
+    const bool nwa = need(K.nw_aux, (long long)H.nw_aux[0]);
+    const bool cig = need(K.cig, H.cig_total);
+    const bool text = need(K.text, H.text_total);
+    const bool junc = need(K.junc, H.junc_total);
+    f = std::min(f, 64.0);
+    auto scale = [&](int64_t &cap) { cap = (int64_t)((double)cap * f * 1.1) + 4096; };
+    // everything downstream of the first overflow has not been counted yet
+    if (seeds) { if (!cands) scale(K.cands); if (!pool) scale(K.pool); }
+    if (seeds || cands || pool) {
+        if (!krecs) scale(K.krecs); if (!nwb) scale(K.nw_ops[0]); if (!nwc) scale(K.nw_ops[1]); if (!nwf) scale(K.nw_flags);
+        if (!nwa) scale(K.nw_aux); if (!cig) scale(K.cig); if (!text) scale(K.text); if (!junc) scale(K.junc);
+    }
+    (void)text; (void)junc;
+}
+
+static void check_ctl_errors(const BatchCtl &H)
+{
+    if (H.err & ERR_CIGAR_POOL) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("CIGAR pool capacity exceeded"));
+    if (H.err & ERR_SORT_SCRATCH) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("seed sort scratch overflow"));
+    if (H.err & ERR_NW_WIDTH) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("NW job wider than the row buffer"));
 }
 
 void add_ms(dartgpu_ctx *c, double *slot, cudaEvent_t a, cudaEvent_t b)
@@ -146,25 +218,33 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
 // ---------------------------------------------------------------------------------------------------
 // stage 1
 // ---------------------------------------------------------------------------------------------------
-void run_seeding(dartgpu_ctx *c, bool fetch)
+void enqueue_seeding(dartgpu_ctx *c)
 {
     const int n = c->n_reads;
     cudaStream_t st = c->stream;
-    c->total_seeds = 0;
-    if (n == 0) { c->o_cand_off.assign(1, 0); c->h_seed_off.reserve(1); c->h_seed_off.p[0] = 0; return; }
+    const Caps &K = c->caps;
+    if (K.seeds >= (1ll << 31)) throw std::make_pair(DARTGPU_ERR_ARG, std::string("batch too large: more than 2^31 seeds, split the batch"));
     c->d_recs.reserve((size_t)n * c->cap_rec);
-    c->d_nrec.reserve(n + 1); c->d_nhits.reserve(n + 1); c->d_ncand.reserve(n + 1);
+    c->d_nrec.reserve(n + 1); c->d_nhits.reserve(n + 1); c->d_ncand.reserve(n + 2);
     c->d_seed_off.reserve(n + 2);
     c->d_big_list.reserve(n + 1); c->d_big_count.reserve(4); c->d_mid_list.reserve(n + 1); c->d_mid_count.reserve(4);
     size_t tmp = scan_tmp_bytes(n);
     c->d_scan_tmp.reserve(tmp + 256);
+    c->d_keys.reserve(K.seeds + 1); c->d_meta.reserve(K.seeds + 1);
+    c->d_cand_begin.reserve(K.seeds + 1); c->d_cand_count.reserve(K.seeds + 1); c->d_cand_score.reserve(K.seeds + 1);
+    // reads with more seeds than fit the shared-memory sort need global scratch: bound = cap_rec * max_dup
+    size_t bound = (size_t)c->cap_rec * c->prm.max_dup, per_cta = 0;
+    if (bound > 4096) { per_cta = 64; while (per_cta < bound) per_cta <<= 1; c->d_big_scratch.reserve(per_cta * sm_count()); }
 
     SeedLaunch a{};
     a.codes = c->d_codes.p; a.dev_off = c->d_dev_off.p; a.rlen = c->d_rlen.p; a.n_reads = n;
     a.cap_rec = c->cap_rec; a.max_dup = c->prm.max_dup; a.max_gaps = c->prm.max_gaps; a.max_intron = c->prm.max_intron;
     a.recs = c->d_recs.p; a.nrec = c->d_nrec.p; a.nhits = c->d_nhits.p; a.seed_off = c->d_seed_off.p;
     a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = c->d_big_count.p; a.mid_list = c->d_mid_list.p; a.mid_count = c->d_mid_count.p;
-    a.stats = c->d_stats.p; a.packed = c->d_packed.p; a.steal = c->d_steal.p;
+    a.ctl = c->d_ctl.p; a.stats = &c->d_ctl.p->stats; a.packed = c->d_packed.p; a.steal = c->d_steal.p;
+    a.keys = c->d_keys.p; a.meta = c->d_meta.p;
+    a.cand_begin = c->d_cand_begin.p; a.cand_count = c->d_cand_count.p; a.cand_score = c->d_cand_score.p;
+    a.big_scratch = c->d_big_scratch.p; a.big_scratch_per_cta = per_cta;
 
     DG_CUDA(cudaMemsetAsync(c->d_nhits.p + n, 0, sizeof(uint32_t), st));
     DG_CUDA(cudaEventRecord(c->ev[2], st));
@@ -172,30 +252,64 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[3], st));
     launch_scan_hits(a, c->d_scan_tmp.p, tmp, st);
-    small_d2h(c->h_total.p, c->d_seed_off.p + n, sizeof(int64_t), st);
-    DG_CUDA(dg_stream_sync(st));
-    const int64_t total = c->h_total.p[0];
-    c->total_seeds = total;
-    c->stats.kernel_launches += 2;
-
-    c->d_keys.reserve(total + 1); c->d_meta.reserve(total + 1);
-    c->d_cand_begin.reserve(total + 1); c->d_cand_count.reserve(total + 1); c->d_cand_score.reserve(total + 1);
-    // reads with more seeds than fit the shared-memory sort need global scratch: bound = cap_rec * max_dup
-    size_t bound = (size_t)c->cap_rec * c->prm.max_dup, per_cta = 0;
-    if (bound > 4096) { per_cta = 64; while (per_cta < bound) per_cta <<= 1; c->d_big_scratch.reserve(per_cta * 148); }
-    a.keys = c->d_keys.p; a.meta = c->d_meta.p;
-    a.cand_begin = c->d_cand_begin.p; a.cand_count = c->d_cand_count.p; a.cand_score = c->d_cand_score.p;
-    a.big_scratch = c->d_big_scratch.p; a.big_scratch_per_cta = per_cta;
-
+    launch_ctl_check(c->d_ctl.p, &c->d_ctl.p->total_seeds, c->d_seed_off.p + n, K.seeds, CAP_SEEDS, st);
     DG_CUDA(cudaEventRecord(c->ev[4], st));
-    launch_expand_locate(c->ix, a, total, st);
+    launch_expand_locate(c->ix, a, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[5], st));
     launch_sort_cluster(c->ix, a, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[6], st));
-    c->stats.kernel_launches += (total > 0 ? 2 : 0) + 3;
+    c->stats.kernel_launches += 9;
+}
 
+// stats of the attempt that went through, from its events and its control block
+static void collect_stats(dartgpu_ctx *c, bool whole_path)
+{
+    const BatchCtl &H = c->h_ctl.p[0];
+    if (c->timed_upload) add_ms(c, &c->stats.ms_h2d, c->ev[0], c->ev[1]);
+    add_ms(c, &c->stats.ms_search, c->ev[2], c->ev[3]);
+    add_ms(c, &c->stats.ms_locate, c->ev[4], c->ev[5]);
+    add_ms(c, &c->stats.ms_sort_cluster, c->ev[5], c->ev[6]);
+    c->stats.ext_steps = H.stats.ext_steps; c->stats.ext_blocks = H.stats.ext_blocks; c->stats.lf_steps = H.stats.lf_steps;
+    c->stats.hits = H.stats.hits; c->stats.seeds = H.stats.seeds; c->stats.search_sector_loads = H.stats.sector_loads;
+    c->total_seeds = H.total_seeds;
+    if (whole_path) {
+        add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
+        add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
+        add_ms(c, &c->stats.ms_nw, c->ev[15], c->ev[16]);
+        add_ms(c, &c->stats.ms_report, c->ev[12], c->ev[13]);
+        add_ms(c, &c->stats.ms_d2h, c->ev[13], c->ev[14]);
+        c->stats.ms_report -= c->stats.ms_kmer + c->stats.ms_nw;   // the phase kernels alone
+        add_ms(c, &c->stats.ms_total_device, c->ev[c->timed_upload ? 0 : 2], c->ev[14]);
+        c->stats.nw_jobs = (uint64_t)H.nw_jobs[0] + (uint64_t)H.nw_jobs[1]; c->stats.nw_cells = H.work[0];
+        c->stats.kmer_jobs = (uint64_t)H.nk; c->stats.kmer_window_bases = H.work[1]; c->stats.kmer_read_bases = H.work[2];
+    } else add_ms(c, &c->stats.ms_total_device, c->ev[2], c->ev[7]);
+}
+
+// stage 1 alone, synchronous (the stage entry points and the kernel-only timing of bench.py)
+static void run_seeding_sync(dartgpu_ctx *c, bool fetch)
+{
+    const int n = c->n_reads;
+    cudaStream_t st = c->stream;
+    c->total_seeds = 0;
+    if (n == 0) { c->o_cand_off.assign(1, 0); c->h_seed_off.reserve(1); c->h_seed_off.p[0] = 0; return; }
+    caps_for_batch(c);
+    for (int attempt = 0;; attempt++) {
+        ctl_begin(c);
+        enqueue_seeding(c);
+        ctl_fetch(c);
+        DG_CUDA(cudaEventRecord(c->ev[7], st));
+        DG_CUDA(dg_stream_sync(st));
+        const BatchCtl &H = c->h_ctl.p[0];
+        if (!H.abort) break;
+        if (attempt >= 8) throw std::make_pair(DARTGPU_ERR_NOMEM, std::string("seed pool keeps overflowing"));
+        caps_grow(c, H);
+    }
+    check_ctl_errors(c->h_ctl.p[0]);
+    c->whole_path = false;
+    collect_stats(c, false);
+    const int64_t total = c->total_seeds;
     if (fetch) {
         c->h_seed_off.reserve(n + 1); c->h_ncand.reserve(n + 1);
         c->h_keys.reserve(total + 1);
@@ -209,22 +323,7 @@ void run_seeding(dartgpu_ctx *c, bool fetch)
             DG_CUDA(cudaMemcpyAsync(c->h_cand_score.p, c->d_cand_score.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         }
         c->stats.d2h_bytes += (n + 1) * 8 + n * 4 + total * 20;
-    }
-    small_d2h(c->h_dstats.p, c->d_stats.p, sizeof(DevStats), st);
-    DG_CUDA(cudaEventRecord(c->ev[7], st));
-    DG_CUDA(dg_stream_sync(st));
-    add_ms(c, &c->stats.ms_h2d, c->ev[0], c->ev[1]);
-    add_ms(c, &c->stats.ms_search, c->ev[2], c->ev[3]);
-    add_ms(c, &c->stats.ms_locate, c->ev[4], c->ev[5]);
-    add_ms(c, &c->stats.ms_sort_cluster, c->ev[5], c->ev[6]);
-    add_ms(c, &c->stats.ms_d2h, c->ev[6], c->ev[7]);
-    add_ms(c, &c->stats.ms_total_device, c->ev[2], c->ev[7]);
-    const DevStats &ds = c->h_dstats.p[0];
-    c->stats.ext_steps = ds.ext_steps; c->stats.ext_blocks = ds.ext_blocks; c->stats.lf_steps = ds.lf_steps;
-    c->stats.hits = ds.hits; c->stats.seeds = ds.seeds;
-    if (fetch) {
-        for (int i = 0; i < n; i++)
-            if (c->h_ncand.p[i] == 0xFFFFFFFFu) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("seed sort scratch overflow"));
+        DG_CUDA(dg_stream_sync(st));
     }
 }
 
@@ -267,17 +366,26 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
     c->h_khits.reserve(n_jobs + 1);
     if (n_jobs == 0) return;
     c->d_kjobs.reserve(n_jobs); c->d_khits.reserve(n_jobs);
+    int64_t cap_recs = 64;                       // the fast path's record demand (k_kmer_prep's formula): known here, the jobs are the caller's
+    for (int i = 0; i < n_jobs; i++) {
+        const int64_t L1 = jobs[i].len1, L2 = jobs[i].len2;
+        if (L1 >= 8 && L2 >= 8) cap_recs += std::min<int64_t>(4096, 2 * (((L2 - 7) * (L1 - 7)) >> 16) + 2 * L1 + 64);
+        c->stats.kmer_window_bases += jobs[i].len2; c->stats.kmer_read_bases += jobs[i].len1;
+    }
+    ctl_begin(c);
+    launch_set_i32(&c->d_ctl.p->nk, n_jobs, st);
     DG_CUDA(cudaMemcpyAsync(c->d_kjobs.p, jobs, (size_t)n_jobs * sizeof(KmerJobDev), cudaMemcpyHostToDevice, st));
     DG_CUDA(cudaEventRecord(c->ev[8], st));
-    launch_kmer(c->ix, codes_dev, c->d_kjobs.p, n_jobs, max_len1, c->d_khits.p, c->kscratch, st);
+    launch_kmer(c->ix, codes_dev, c->d_kjobs.p, &c->d_ctl.p->nk, n_jobs, max_len1, c->d_khits.p, c->kscratch, c->d_ctl.p, cap_recs, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[9], st));
     DG_CUDA(cudaMemcpyAsync(c->h_khits.p, c->d_khits.p, (size_t)n_jobs * sizeof(dartgpu_kmer_hit), cudaMemcpyDeviceToHost, st));
+    ctl_fetch(c);
     DG_CUDA(dg_stream_sync(st));
+    if (c->h_ctl.p[0].abort) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("8-mer record pool overflow"));
     add_ms(c, &c->stats.ms_kmer, c->ev[8], c->ev[9]);
     c->stats.kernel_launches += KMER_LAUNCHES;
     c->stats.kmer_jobs += n_jobs;
-    for (int i = 0; i < n_jobs; i++) { c->stats.kmer_window_bases += jobs[i].len2; c->stats.kmer_read_bases += jobs[i].len1; }
     c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(KmerJobDev);
     c->stats.d2h_bytes += (uint64_t)n_jobs * sizeof(dartgpu_kmer_hit);
 }
@@ -290,29 +398,36 @@ void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs
     if (n_jobs == 0) return;
     int64_t ops_total = 0, flag_total = 0;
     int max_n = 0;
-    bool multi_strip = false;
     for (int i = 0; i < n_jobs; i++) {
-        jobs[i].op_off = ops_total; jobs[i].flag_off = flag_total;
-        ops_total += jobs[i].m + jobs[i].n;
+        ops_total += std::max(jobs[i].m, 0) + std::max(jobs[i].n, 0);
         flag_total += (int64_t)jobs[i].m * ((jobs[i].n + 15) >> 4);
         max_n = std::max(max_n, jobs[i].n);
-        multi_strip |= jobs[i].m > 32;
         c->stats.nw_cells += (uint64_t)jobs[i].m * jobs[i].n;
     }
     c->stats.nw_jobs += n_jobs;
-    size_t rb_per_warp = multi_strip ? (size_t)2 * (max_n + 1) : 0;
+    const size_t rb_per_warp = (size_t)2 * (max_n + 1);
     c->d_njobs.reserve(n_jobs); c->d_nw_flags.reserve(flag_total + 1); c->d_nw_ops.reserve(ops_total + 1);
     c->d_nw_nops.reserve(n_jobs);
     c->d_nw_rowbuf.reserve(rb_per_warp * nw_grid_warps() + 1);
     c->h_nw_ops.reserve(ops_total + 1); c->h_nw_nops.reserve(n_jobs);
+    ctl_begin(c);
+    launch_set_i32(&c->d_ctl.p->nw_jobs[1], n_jobs, st);
     DG_CUDA(cudaMemcpyAsync(c->d_njobs.p, jobs, (size_t)n_jobs * sizeof(NwJobDev), cudaMemcpyHostToDevice, st));
+    NwRound R{};
+    R.jobs = c->d_njobs.p; R.n_jobs = &c->d_ctl.p->nw_jobs[1]; R.cap_jobs = n_jobs; R.round = 1; R.with_aux = 0;
+    R.cap_ops = ops_total; R.cap_flags = flag_total; R.cap_aux = 0;
+    R.flags = c->d_nw_flags.p; R.ops = c->d_nw_ops.p; R.nops = c->d_nw_nops.p; R.rowbuf = c->d_nw_rowbuf.p; R.rowbuf_per_warp = rb_per_warp;
     DG_CUDA(cudaEventRecord(c->ev[10], st));
-    launch_nw(c->ix, codes_dev, c->d_njobs.p, n_jobs, c->d_nw_flags.p, c->d_nw_rowbuf.p, rb_per_warp, c->d_nw_ops.p, c->d_nw_nops.p, c->nwscratch, st);
+    launch_nw(c->ix, codes_dev, R, c->d_ctl.p, c->nwscratch, st);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[11], st));
     DG_CUDA(cudaMemcpyAsync(c->h_nw_ops.p, c->d_nw_ops.p, ops_total, cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaMemcpyAsync(c->h_nw_nops.p, c->d_nw_nops.p, (size_t)n_jobs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaMemcpyAsync(jobs, c->d_njobs.p, (size_t)n_jobs * sizeof(NwJobDev), cudaMemcpyDeviceToHost, st));   // the slices the device handed out
+    ctl_fetch(c);
     DG_CUDA(dg_stream_sync(st));
+    if (c->h_ctl.p[0].abort) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("NW pool overflow"));
+    check_ctl_errors(c->h_ctl.p[0]);
     add_ms(c, &c->stats.ms_nw, c->ev[10], c->ev[11]);
     c->stats.kernel_launches += NW_LAUNCHES;
     c->stats.h2d_bytes += (uint64_t)n_jobs * sizeof(NwJobDev);
@@ -323,7 +438,7 @@ void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs
 #pragma omp parallel for schedule(static) num_threads(threads)
     for (int i = 0; i < n_jobs; i++) {
         int k = c->h_nw_nops.p[i];
-        const uint8_t *src = c->h_nw_ops.p + jobs[i].op_off + jobs[i].m + jobs[i].n - k; // written right-aligned by the traceback
+        const uint8_t *src = c->h_nw_ops.p + jobs[i].op_off + std::max(jobs[i].m, 0) + std::max(jobs[i].n, 0) - k; // written right-aligned by the traceback
         if (k) memcpy(c->o_ops.data() + c->o_op_off[i], src, k);
     }
 }
@@ -520,6 +635,9 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
             throw std::make_pair(DARTGPU_ERR_INDEX, std::string("a symbol occurs 2^32 times or more: interval widths would not fit 32 bits"));
     if (v->seq_len != 2 * (uint64_t)v->l_pac)
         throw std::make_pair(DARTGPU_ERR_INDEX, std::string("index is not a forward+reverse-complement (FMD) index"));
+    // a seed is one 64-bit key, gPos << 31 | rPos << 15 | len (dartgpu_internal.h seed_key): 33 bits of text coordinate
+    if (v->seq_len >= (1ull << 33))
+        throw std::make_pair(DARTGPU_ERR_INDEX, std::string("text of 2^33 symbols or more (genome over 4.29 Gbp): coordinates do not fit the 33-bit field of the seed key"));
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); throw std::make_pair(DARTGPU_ERR_NO_DEVICE, std::string("no CUDA device: libdartgpu has no CPU fallback")); }
@@ -531,7 +649,8 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
     c->shared = load_shared_index(c->device, v, c->stream);
     c->ix = c->shared->ix;
     c->G = c->shared->G;
-    c->d_stats.reserve(1); c->h_total.reserve(2); c->h_dstats.reserve(1); c->d_steal.reserve(4);
+    c->d_ctl.reserve(1); c->h_ctl.reserve(1); c->d_steal.reserve(4);
+    DG_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventBlockingSync | cudaEventDisableTiming));
     DG_CUDA(dg_stream_sync(c->stream));
 }
 
@@ -644,7 +763,9 @@ void dartgpu_destroy(dartgpu_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->in_flight) cudaStreamSynchronize(c->stream);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->done) cudaEventDestroy(c->done);
     if (c->dpipe) free_device_pipe(c->dpipe);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -671,11 +792,13 @@ int dartgpu_set_stream(dartgpu_ctx *c, void *s)
 int dartgpu_seed_and_cluster(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_seeds *out)
 {
     if (!c || !reads || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
     return guarded(c, [&] {
         Timer t;
         stats_begin(c);
         upload_reads(c, reads);
-        run_seeding(c, true);
+        c->timed_upload = true;
+        run_seeding_sync(c, true);
         unpack_seeds(c, out);
         c->stats.ms_host = t.ms();
     });
@@ -684,17 +807,20 @@ int dartgpu_seed_and_cluster(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu
 int dartgpu_upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
 {
     if (!c || !reads) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
     return guarded(c, [&] { stats_begin(c); upload_reads(c, reads); DG_CUDA(dg_stream_sync(c->stream)); });
 }
 
 int dartgpu_seed_and_cluster_resident(dartgpu_ctx *c)
 {
     if (!c) return DARTGPU_ERR_ARG;
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
     return guarded(c, [&] {
         uint64_t rb = c->stats.read_bases;
         stats_begin(c);
         c->stats.read_bases = rb;
-        run_seeding(c, false);
+        c->timed_upload = false;
+        run_seeding_sync(c, false);
     });
 }
 
@@ -747,42 +873,108 @@ int dartgpu_nw_align(dartgpu_ctx *c, const char *bases, int64_t n_bases, const d
     });
 }
 
+// ---- the whole per-read path: submit (enqueue everything, return) / wait (sleep until the batch is done) ----
+namespace dartgpu {
+// everything of one attempt behind the (already enqueued or resident) read upload; records the `done` event
+static void enqueue_whole_path(dartgpu_ctx *c)
+{
+    ctl_begin(c);
+    enqueue_seeding(c);
+    enqueue_pipeline(c);
+    ctl_fetch(c);
+    DG_CUDA(cudaEventRecord(c->done, c->stream));
+}
+
+static void submit_batch(dartgpu_ctx *c, const dartgpu_reads *reads)
+{   // reads == nullptr: the batch uploaded with dartgpu_upload_reads
+    Timer t;
+    uint64_t rb = c->stats.read_bases;
+    stats_begin(c);
+    if (reads) upload_reads(c, reads); else c->stats.read_bases = rb;
+    c->timed_upload = reads != nullptr;
+    c->whole_path = true;
+    c->attempts = 0;
+    if (c->n_reads > 0) {
+        caps_for_batch(c);
+        enqueue_whole_path(c);
+    }
+    c->in_flight = true;
+    c->t_submit_ms = t.ms();
+}
+
+static void wait_batch(dartgpu_ctx *c, dartgpu_map_result *out)
+{
+    Timer t;
+    c->in_flight = false;
+    if (c->n_reads == 0) { *out = dartgpu_map_result{nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0}; return; }
+    for (;;) {
+        DG_CUDA(cudaEventSynchronize(c->done));            // the batch's one wait: a sleeping thread, not a spinning one
+        const BatchCtl &H = c->h_ctl.p[0];
+        if (!H.abort) break;
+        // a pool was too small (first batch of a context, or a batch unlike the ones before): grow it and run the batch again
+        if (++c->attempts > 12) throw std::make_pair(DARTGPU_ERR_NOMEM, std::string("device pools keep overflowing"));
+        caps_grow(c, H);
+        const uint64_t keep_launches = c->stats.kernel_launches;
+        enqueue_whole_path(c);
+        c->stats.kernel_launches = keep_launches;        // only the attempt that goes through is counted
+    }
+    check_ctl_errors(c->h_ctl.p[0]);
+    finish_pipeline(c, out);
+    collect_stats(c, true);
+    c->stats.ms_host = c->t_submit_ms + t.ms();
+}
+} // namespace dartgpu
+
+int dartgpu_submit(dartgpu_ctx *c, const dartgpu_reads *reads)
+{
+    if (!c || !reads) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
+    if (c->prm.pair_end && (reads->n_reads & 1)) return fail(c, DARTGPU_ERR_ARG, "paired-end batch with an odd number of reads");
+    return guarded(c, [&] { submit_batch(c, reads); });
+}
+
+int dartgpu_submit_resident(dartgpu_ctx *c)
+{
+    if (!c) return DARTGPU_ERR_ARG;
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
+    if (c->prm.pair_end && (c->n_reads & 1)) return fail(c, DARTGPU_ERR_ARG, "paired-end batch with an odd number of reads");
+    return guarded(c, [&] { submit_batch(c, nullptr); });
+}
+
+int dartgpu_wait(dartgpu_ctx *c, dartgpu_map_result *out)
+{
+    if (!c || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (!c->in_flight) return fail(c, DARTGPU_ERR_ARG, "no batch in flight on this context");
+    int rc = guarded(c, [&] { wait_batch(c, out); });
+    if (rc != DARTGPU_OK) { c->in_flight = false; cudaStreamSynchronize(c->stream); cudaGetLastError(); }
+    return rc;
+}
+
 int dartgpu_map_reads(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out)
 {
     if (!c || !reads || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
-    if (c->prm.pair_end && (reads->n_reads & 1)) return fail(c, DARTGPU_ERR_ARG, "paired-end batch with an odd number of reads");
-    return guarded(c, [&] {
-        Timer t;
-        stats_begin(c);
-        upload_reads(c, reads);
-        run_seeding(c, false);
-        run_pipeline_device(c, out);
-        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_h2d + c->stats.ms_report;
-        c->stats.ms_host = t.ms();
-    });
+    int rc = dartgpu_submit(c, reads);
+    return rc != DARTGPU_OK ? rc : dartgpu_wait(c, out);
 }
 
 int dartgpu_map_reads_resident(dartgpu_ctx *c, const dartgpu_reads *reads, dartgpu_map_result *out)
 {
     if (!c || !reads || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
     if (reads->n_reads != c->n_reads) return fail(c, DARTGPU_ERR_ARG, "batch differs from the uploaded one");
-    if (c->prm.pair_end && (reads->n_reads & 1)) return fail(c, DARTGPU_ERR_ARG, "paired-end batch with an odd number of reads");
-    return guarded(c, [&] {
-        Timer t;
-        uint64_t rb = c->stats.read_bases;
-        stats_begin(c);
-        c->stats.read_bases = rb;
-        run_seeding(c, false);
-        run_pipeline_device(c, out);
-        c->stats.ms_total_device += c->stats.ms_kmer + c->stats.ms_nw + c->stats.ms_report;
-        c->stats.ms_host = t.ms();
-    });
+    int rc = dartgpu_submit_resident(c);
+    return rc != DARTGPU_OK ? rc : dartgpu_wait(c, out);
 }
 
 int dartgpu_measure_int32_peak(dartgpu_ctx *c, double *ops_per_second)
 {
     if (!c || !ops_per_second) return DARTGPU_ERR_ARG;
     return guarded(c, [&] { *ops_per_second = measure_int32_ops_per_second(c->stream); });
+}
+
+int dartgpu_measure_l2_peak(dartgpu_ctx *c, uint64_t table_bytes, double *bytes_per_second)
+{
+    if (!c || !bytes_per_second || table_bytes < 64) return DARTGPU_ERR_ARG;
+    return guarded(c, [&] { *bytes_per_second = measure_l2_gather_bytes_per_second(c->stream, (size_t)table_bytes); });
 }
 
 int dartgpu_get_stats(const dartgpu_ctx *c, dartgpu_stats *out)

@@ -30,6 +30,15 @@ struct SharedIndex {
 };
 } // namespace dartgpu
 
+namespace dartgpu {
+// Capacities of the per-batch device pools whose fill is only known on the device (BatchCtl, dartgpu_internal.h).
+// They only ever grow: from the batch's size the first time, from the control block of an aborted batch afterwards.
+struct Caps {
+    int64_t seeds = 0, cands = 0, pool = 0, krecs = 0, cig = 0, text = 0, junc = 0;
+    int64_t nw_ops[2] = {0, 0}, nw_flags = 0, nw_aux = 0;
+};
+} // namespace dartgpu
+
 struct dartgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -62,10 +71,15 @@ struct dartgpu_ctx {
     dartgpu::DevBuf<uint64_t> d_keys, d_big_scratch;
     dartgpu::DevBuf<int32_t> d_cand_begin, d_cand_count, d_cand_score;
     dartgpu::DevBuf<uint8_t> d_scan_tmp;
-    dartgpu::DevBuf<dartgpu::DevStats> d_stats;
-    dartgpu::PinBuf<int64_t> h_total;
-    dartgpu::PinBuf<dartgpu::DevStats> h_dstats;
+    dartgpu::DevBuf<dartgpu::BatchCtl> d_ctl;     // the batch's control block on the device ...
+    dartgpu::PinBuf<dartgpu::BatchCtl> h_ctl;     // ... and its copy, read once per batch
+    dartgpu::Caps caps;
     int64_t total_seeds = 0;
+    // ---- the batch in flight (dartgpu_submit .. dartgpu_wait) ----
+    bool in_flight = false, whole_path = false, timed_upload = false;
+    int attempts = 0;
+    cudaEvent_t done = nullptr;                   // blocking-sync event recorded behind the batch
+    double t_submit_ms = 0;
 
     // seeding results on the host
     dartgpu::PinBuf<int64_t> h_seed_off;
@@ -105,7 +119,7 @@ struct dartgpu_ctx {
 
     // ---- measurement ----
     dartgpu_stats stats{};
-    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev[20] = {};
 };
 
 namespace dartgpu {
@@ -115,13 +129,14 @@ void add_ms(dartgpu_ctx *c, double *slot, cudaEvent_t a, cudaEvent_t b);
 
 // stage runners; all throw CudaError / std::exception on failure
 void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads);          // encode + H2D
-void run_seeding(dartgpu_ctx *c, bool fetch_results);                    // search, locate, sort+cluster [, D2H + unpack]
+void enqueue_seeding(dartgpu_ctx *c);                                     // search, locate, sort+cluster: enqueued, nothing waits
 // k-mer jobs whose fragments live in `codes_dev` (device). Results in c->h_khits (valid after return).
 void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, int n_jobs, int max_len1);
-// NW jobs (op_off / flag_off are filled here). Results: c->o_op_off / c->o_ops (compacted, left-to-right columns).
+// NW jobs (op_off / flag_off are assigned on the device). Results: c->o_op_off / c->o_ops (compacted, left-to-right columns).
 void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs);
-// the whole per-read path over the uploaded batch
-void run_pipeline_device(dartgpu_ctx *c, dartgpu_map_result *out);                              // device orchestration
+// the whole per-read path over the uploaded batch: device orchestration, enqueued behind the seeding kernels
+void enqueue_pipeline(dartgpu_ctx *c);
+void finish_pipeline(dartgpu_ctx *c, dartgpu_map_result *out);          // after the batch's synchronisation
 void free_device_pipe(void *p);
 
 struct Timer {

@@ -65,7 +65,28 @@ __host__ __device__ inline int key_len(uint64_t k) { return (int)(k & 0x7FFF); }
 enum { CODE_OTHER = 4, CODE_N = 5 };
 
 struct DevStats {            // device-side work counters (see dartgpu_stats)
-    unsigned long long ext_steps, ext_blocks, lf_steps, hits, seeds;
+    unsigned long long ext_steps, ext_blocks, lf_steps, hits, seeds, sector_loads;
+};
+
+// Control block of ONE batch, in device memory: every count the host used to read back between kernel launches
+// (round 1: ~20 stream synchronisations per batch, which tied every context to a spinning host thread and capped 8-GPU
+// weak scaling at 0.58) now stays here.  Kernels read their loop bounds from it, pools have host-chosen CAPACITIES, and a
+// kernel that would exceed one sets `abort` instead: everything enqueued behind it returns at once, and the host -- which
+// looks at this block exactly once per batch, together with the results -- grows the pool and runs the batch again.
+// In steady state (batches of similar size) no batch is ever repeated and the host synchronises once per batch.
+enum { CAP_SEEDS = 1, CAP_CANDS = 2, CAP_POOL = 4, CAP_KRECS = 8, CAP_NW_B = 16, CAP_NW_C = 32, CAP_CIG = 64, CAP_TEXT = 128,
+       CAP_JUNC = 256 };
+enum { ERR_CIGAR_POOL = 1, ERR_SORT_SCRATCH = 2, ERR_NW_WIDTH = 4 };
+struct BatchCtl {
+    long long total_seeds, ncand, nrep, pool_total, cig_total, text_total, junc_total, kmer_recs;
+    unsigned long long nw_ops[2], nw_flags[2], nw_aux[2];   // pool use of the two NW rounds (B: gap flanks, C: non-simple pairs)
+    int32_t nk, nw_jobs[2], nw_small[2];                    // job-queue lengths; jobs of the thread-per-alignment class
+    int32_t nw_max_n[2];
+    int32_t abort;                                          // CAP_* bits: a capacity was exceeded, the batch must be re-run
+    int32_t err;                                            // ERR_* bits: internal invariants that must never fire
+    int32_t pad;
+    unsigned long long work[4];                             // [0] NW cells, [1] 8-mer window bases, [2] 8-mer read bases
+    DevStats stats;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -101,13 +122,13 @@ template <class T> struct PinBuf {
     ~PinBuf() { release(); }
 };
 
-// Host-side wait for a stream.  By default the driver spins, which is the lowest latency while every waiting host thread has
-// a core of its own; with DARTGPU_SYNC=block the thread sleeps on a blocking event instead, so that many contexts (several
-// per GPU x 8 GPUs on a 16-core host) do not steal the cores the other threads need to launch their kernels.
+// Host-side wait for a stream.  The waiting thread SLEEPS on a blocking event: with one wait per batch (BatchCtl above) the
+// wake-up latency is paid once per batch instead of ~20 times, and one host thread per GPU is enough to keep several batches
+// in flight without stealing the cores the other ranks' threads need.  DARTGPU_SYNC=spin restores the spinning wait.
 inline cudaError_t dg_stream_sync(cudaStream_t st)
 {
-    static const bool block = [] { const char *e = getenv("DARTGPU_SYNC"); return e && !strcmp(e, "block"); }();
-    if (!block) return cudaStreamSynchronize(st);
+    static const bool spin = [] { const char *e = getenv("DARTGPU_SYNC"); return e && !strcmp(e, "spin"); }();
+    if (spin) return cudaStreamSynchronize(st);
     thread_local cudaEvent_t ev = nullptr;
     thread_local int ev_dev = -1;
     int dev = 0;
@@ -126,6 +147,10 @@ inline cudaError_t dg_stream_sync(cudaStream_t st)
 // kernel launchers (each file owns its kernels; all work is enqueued on `st`)
 // ---------------------------------------------------------------------------------------------------
 // index_device.cu
+int sm_count();                                   // SMs of the current device (cached per device, thread-safe)
+void launch_set_i32(int32_t *dst, int32_t v, cudaStream_t st);
+// dst (a field of *ctl) = *src; sets `bit` in ctl->abort when the value exceeds cap
+void launch_ctl_check(BatchCtl *ctl, long long *dst, const int64_t *src, int64_t cap, int bit, cudaStream_t st);
 void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t st);   // bytes: multiple of 4, pinned destination
 void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *occ, uint64_t n_blocks32, cudaStream_t st);
 // sa_file: the reference's sampled SA (every sa_intv-th entry, entry 0 = -1) on the device; out: every 2^shift-th entry
@@ -152,25 +177,34 @@ struct SeedLaunch {
     uint32_t *big_list; uint32_t *big_count;                    // reads with more than 32 seeds (one block each)
     uint64_t *big_scratch; size_t big_scratch_per_cta;          // global sort scratch for reads that exceed smem
     DevStats *stats;
+    BatchCtl *ctl;                                              // ctl->total_seeds bounds the per-hit kernels
 };
 void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st);
 void launch_scan_hits(const SeedLaunch &a, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t scan_tmp_bytes(int n);
-void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, int64_t total_seeds, cudaStream_t st);
+void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st);   // hit count: a.ctl->total_seeds
 void launch_sort_cluster(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st);
 void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 
 // nw_kernel.cu
 struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int64_t aux_off; int32_t m, n; };
-struct NwScratch {         // sort buffers of the thread-per-job NW class, owned by the context
-    DevBuf<uint32_t> keys, vals, keys2, vals2, counter;
-    DevBuf<uint8_t> tmp;
+constexpr int NW_BINS = 64 * 64 + 1;   // shape classes (n, m) of the thread-per-alignment kernel + one for everything larger
+struct NwScratch {         // shape-class counting sort of the job queue, owned by the context
+    DevBuf<uint32_t> hist, bin_start, bin_cur, order, counter;
 };
-constexpr int NW_LAUNCHES = 4;     // sort keys, radix sort (counted once), k_nw_thread, k_nw
-void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,
-               uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, NwScratch &scratch, cudaStream_t st);
+struct NwRound {           // one batched NW launch over a job queue whose length lives on the device
+    NwJobDev *jobs; const int32_t *n_jobs; int cap_jobs;
+    int round;             // 0: phase B (gap flanks, with Rvec/Lvec scratch per pair), 1: phase C / the stage entry point
+    int with_aux;
+    int64_t cap_ops, cap_flags, cap_aux;
+    uint32_t *flags; uint8_t *ops; int32_t *nops;
+    int32_t *rowbuf; size_t rowbuf_per_warp;   // ints per warp: 2 * (widest job + 1)
+};
+constexpr int NW_LAUNCHES = 5;     // prepare, bins, scatter, k_nw_thread, k_nw
+void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwRound &R, BatchCtl *ctl, NwScratch &scratch, cudaStream_t st);
 int nw_grid_warps();
 double measure_int32_ops_per_second(cudaStream_t st);
+double measure_l2_gather_bytes_per_second(cudaStream_t st, size_t table_bytes);
 
 // kmer_kernel.cu
 struct KmerJobDev { int64_t s1_off; int64_t gpos; int32_t len1, len2; };
@@ -178,10 +212,10 @@ struct KmerScratch {       // device scratch of the k-mer fast path, owned by th
     DevBuf<uint32_t> ntiles, cap, count, recs, heavy_list, heavy_count;
     DevBuf<int64_t> tile_off, rec_off;
     DevBuf<uint8_t> scan_tmp;
-    PinBuf<int64_t> h_total;
 };
-constexpr int KMER_LAUNCHES = 6;   // prep, 2 scans (counted as one each), scan, walk, ring
-void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *jobs, int n_jobs, int max_len1,
-                 dartgpu_kmer_hit *out, KmerScratch &scratch, cudaStream_t st);
+constexpr int KMER_LAUNCHES = 7;   // prep, 2 scans (counted as one each), check, scan, walk, ring
+// job-queue length on the device (*n_jobs <= cap_jobs); the record pool holds cap_recs records (CAP_KRECS on overflow)
+void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *jobs, const int32_t *n_jobs, int cap_jobs, int max_len1,
+                 dartgpu_kmer_hit *out, KmerScratch &scratch, BatchCtl *ctl, int64_t cap_recs, cudaStream_t st);
 
 } // namespace dartgpu

@@ -188,7 +188,7 @@ struct SuffixLess {
     }
 };
 
-static int grid_for(uint64_t n, int threads = 256) { uint64_t g = (n + threads - 1) / threads; return (int)std::max<uint64_t>(1, std::min<uint64_t>(g, 148 * 16)); }
+static int grid_for(uint64_t n, int threads = 256) { uint64_t g = (n + threads - 1) / threads; return (int)std::max<uint64_t>(1, std::min<uint64_t>(g, (uint64_t)sm_count() * 16)); }
 
 static void write_file(const std::string &fn, const std::vector<std::pair<const void *, size_t>> &parts)
 {

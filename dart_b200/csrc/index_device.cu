@@ -4,7 +4,38 @@
 #include "dartgpu_internal.h"
 #include "rank.cuh"
 
+#include <atomic>
+
 namespace dartgpu {
+
+int sm_count()
+{   // per device: a process drives several GPUs from several threads (round-1 advice: function-local statics keyed to
+    // the first device were a data race and sized grids for the wrong GPU)
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 1; }
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+__global__ void k_set_i32(int32_t *dst, int32_t v) { *dst = v; }
+void launch_set_i32(int32_t *dst, int32_t v, cudaStream_t st) { k_set_i32<<<1, 1, 0, st>>>(dst, v); }
+
+__global__ void k_ctl_check(BatchCtl *ctl, long long *dst, const int64_t *src, int64_t cap, int bit)
+{
+    const long long v = *src;
+    *dst = v;
+    if (v > cap) atomicOr(&ctl->abort, bit);
+}
+void launch_ctl_check(BatchCtl *ctl, long long *dst, const int64_t *src, int64_t cap, int bit, cudaStream_t st)
+{
+    k_ctl_check<<<1, 1, 0, st>>>(ctl, dst, src, cap, bit);
+}
 
 // BWA block (128 symbols) = 8 words of counts (4 x u64, little endian) + 8 words of symbols (16 per word, first symbol
 // in the top bits).  Output: two Occ32 blocks (rank.cuh) per BWA block; the second one's counts include the first half.
@@ -42,7 +73,7 @@ __global__ void k_relayout_occ32(const uint32_t *__restrict__ w, uint64_t n_word
 void launch_relayout_occ32(const uint32_t *bwt_words, uint64_t n_words, Occ32 *occ, uint64_t n_blocks32, cudaStream_t st)
 {
     uint64_t want = (n_blocks32 + 1 + 255) / 256;
-    int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    int grid = (int)(want < sm_count() * 16 ? want : sm_count() * 16);
     if (grid < 1) grid = 1;
     k_relayout_occ32<<<grid, 256, 0, st>>>(bwt_words, n_words, occ, n_blocks32);
 }
@@ -80,7 +111,7 @@ void launch_build_ktab(const DevIndex &ix, int K, KmerStart *out, KmerStart *tmp
     for (int j = 0; j < K; j++) {
         const uint64_t n_next = 1ull << (2 * (j + 1));
         uint64_t want = (n_next + 255) / 256;
-        int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+        int grid = (int)(want < sm_count() * 16 ? want : sm_count() * 16);
         k_ktab_level<<<grid, 256, 0, st>>>(ix, j, bufs[(j + 1) & 1], bufs[j & 1]);
     }
 }
@@ -120,7 +151,7 @@ __global__ void k_sa_densify(DevIndex ix, const uint64_t *__restrict__ sa_file, 
 void launch_sa_densify(const DevIndex &ix, const uint64_t *sa_file, uint64_t sa_intv, uint64_t n_sa_file, void *out, cudaStream_t st)
 {
     uint64_t want = (n_sa_file + 255) / 256;
-    int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+    int grid = (int)(want < sm_count() * 32 ? want : sm_count() * 32);
     if (grid < 1) grid = 1;
     if (ix.sa_wide) k_sa_densify<uint64_t><<<grid, 256, 0, st>>>(ix, sa_file, sa_intv, n_sa_file, (uint64_t *)out);
     else k_sa_densify<uint32_t><<<grid, 256, 0, st>>>(ix, sa_file, sa_intv, n_sa_file, (uint32_t *)out);
@@ -153,7 +184,7 @@ void launch_build_ref2(const uint8_t *pac, uint32_t *ref2, int64_t G, cudaStream
 {
     int64_t n_words = (2 * G + 15) / 16 + 2; // two guard words so 64-bit window reads never run off the end
     int64_t blocks = (n_words + 255) / 256;
-    int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    int grid = (int)(blocks < sm_count() * 16 ? blocks : sm_count() * 16);
     if (grid < 1) grid = 1;
     k_build_ref2<<<grid, 256, 0, st>>>(pac, ref2, G, n_words);
 }
@@ -242,13 +273,13 @@ void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t st
 
 void launch_read_layout(const int64_t *off, int n, int32_t *rlen, uint32_t *padded, cudaStream_t st)
 {
-    int grid = (n + 1 + 255) / 256; if (grid > 148 * 8) grid = 148 * 8;
+    int grid = (n + 1 + 255) / 256; if (grid > sm_count() * 8) grid = sm_count() * 8;
     k_read_layout<<<grid, 256, 0, st>>>(off, n, rlen, padded);
 }
 void launch_encode_reads(const uint8_t *raw, const int64_t *off, const int64_t *dev_off, int n, uint8_t *codes, uint2 *packed, cudaStream_t st)
 {
     int64_t want = ((int64_t)n * 8 + 255) / 256;
-    int grid = (int)(want < 148 * 16 ? want : 148 * 16); if (grid < 1) grid = 1;
+    int grid = (int)(want < sm_count() * 16 ? want : sm_count() * 16); if (grid < 1) grid = 1;
     k_encode_reads<<<grid, 256, 0, st>>>(raw, off, dev_off, n, codes, packed);
 }
 

@@ -45,8 +45,9 @@ __device__ __forceinline__ uint32_t genome_kmer(const DevIndex &ix, int64_t p)
 __global__ void __launch_bounds__(KMER_THREADS)
 k_kmer(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs,
        const uint32_t *__restrict__ job_list, const uint32_t *__restrict__ n_listed,
-       int tab_cap, int ring, dartgpu_kmer_hit *out)
+       int tab_cap, int ring, const BatchCtl *__restrict__ ctl, dartgpu_kmer_hit *out)
 {
+    if (ctl->abort) return;
     extern __shared__ uint32_t smem[];
     uint32_t *tab = smem;                       // tab_cap entries: id << 16 | read position
     uint32_t *cnt = tab + tab_cap;              // ring of per-diagonal aggregates
@@ -225,14 +226,20 @@ constexpr int KS_THREADS = 256, KS_PPT = 16, KS_TILE = KS_THREADS * KS_PPT, KS_C
 constexpr int KS_HASH = 2048;                    // >= 2 x the most 8-mers a gap can have (DARTGPU_MAX_RLEN - 7)
 constexpr uint32_t KS_CAP_MAX = 4096, KS_EMPTY = 0xFFFFFFFFu;
 
-__global__ void k_kmer_prep(const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, int n_jobs, int tab_cap, uint32_t cap_max,
-                            uint32_t *ntiles, uint32_t *cap, uint32_t *count, uint32_t *heavy_list, uint32_t *heavy_count,
-                            dartgpu_kmer_hit *out)
+__global__ void k_kmer_prep(const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, const int32_t *__restrict__ n_jobs_p, int cap_jobs,
+                            int tab_cap, uint32_t cap_max, uint32_t *ntiles, uint32_t *cap, uint32_t *count, uint32_t *heavy_list,
+                            uint32_t *heavy_count, BatchCtl *ctl, dartgpu_kmer_hit *out)
 {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= n_jobs; j += gridDim.x * blockDim.x) {
-        if (j == n_jobs) { ntiles[j] = 0; cap[j] = 0; continue; }
+    if (ctl->abort) return;
+    const int n_jobs = min(*n_jobs_p, cap_jobs);
+    unsigned long long w_sum = 0, r_sum = 0;
+    // the two prefix sums behind this kernel run over the queue's CAPACITY (its length is only known on the device):
+    // slots beyond the length count zero
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= cap_jobs; j += gridDim.x * blockDim.x) {
+        if (j >= n_jobs) { ntiles[j] = 0; cap[j] = 0; continue; }
         const KmerJobDev J = jobs[j];
         const int L1 = J.len1, L2 = J.len2;
+        w_sum += (unsigned long long)L2; r_sum += (unsigned long long)L1;
         uint32_t nt = 0, cp = 0;
         if (L1 >= 8 && L2 >= 8 && L1 <= tab_cap) {
             bool plain = L1 <= DARTGPU_MAX_RLEN && (int64_t)L1 + L2 < (1 << 22);
@@ -246,15 +253,19 @@ __global__ void k_kmer_prep(const uint8_t *__restrict__ codes, const KmerJobDev 
         } else { out[j].rpos = 0; out[j].gpos = 0; out[j].len = 0; }
         ntiles[j] = nt; cap[j] = cp; count[j] = 0;
     }
+    for (int d = 16; d > 0; d >>= 1) { w_sum += __shfl_xor_sync(FULLK, w_sum, d); r_sum += __shfl_xor_sync(FULLK, r_sum, d); }
+    if ((threadIdx.x & 31) == 0 && (w_sum | r_sum)) { atomicAdd(&ctl->work[1], w_sum); atomicAdd(&ctl->work[2], r_sum); }
 }
 
 __device__ __forceinline__ uint32_t ks_hash(uint32_t id) { return ((id * 40503u) >> 4) & (KS_HASH - 1); }
 
 __global__ void __launch_bounds__(KS_THREADS)
-k_kmer_scan(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, int n_jobs,
+k_kmer_scan(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__restrict__ jobs, const int32_t *__restrict__ n_jobs_p, int cap_jobs,
             const int64_t *__restrict__ chunk_off, const int64_t *__restrict__ rec_off, const uint32_t *__restrict__ cap,
-            uint32_t *count, uint32_t *recs)
+            uint32_t *count, uint32_t *recs, const BatchCtl *__restrict__ ctl)
 {
+    if (ctl->abort) return;
+    const int n_jobs = min(*n_jobs_p, cap_jobs);
     __shared__ uint32_t bm[2048];
     __shared__ uint32_t ht[KS_HASH];
     __shared__ int s_job;
@@ -338,10 +349,12 @@ k_kmer_scan(DevIndex ix, const uint8_t *__restrict__ codes, const KmerJobDev *__
 }
 
 __global__ void __launch_bounds__(128)
-k_kmer_walk(const KmerJobDev *__restrict__ jobs, int n_jobs, const int64_t *__restrict__ rec_off, const uint32_t *__restrict__ cap,
-            const uint32_t *__restrict__ count, const uint32_t *__restrict__ recs, uint32_t *heavy_list, uint32_t *heavy_count,
-            dartgpu_kmer_hit *out)
+k_kmer_walk(const KmerJobDev *__restrict__ jobs, const int32_t *__restrict__ n_jobs_p, int cap_jobs, const int64_t *__restrict__ rec_off,
+            const uint32_t *__restrict__ cap, const uint32_t *__restrict__ count, const uint32_t *__restrict__ recs, uint32_t *heavy_list,
+            uint32_t *heavy_count, const BatchCtl *__restrict__ ctl, dartgpu_kmer_hit *out)
 {
+    if (ctl->abort) return;
+    const int n_jobs = min(*n_jobs_p, cap_jobs);
     __shared__ uint32_t sm[KS_CAP_MAX];
     const int tid = threadIdx.x;
     for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -391,36 +404,37 @@ k_kmer_walk(const KmerJobDev *__restrict__ jobs, int n_jobs, const int64_t *__re
 }
 
 
-void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *jobs, int n_jobs, int max_len1,
-                 dartgpu_kmer_hit *out, KmerScratch &S, cudaStream_t st)
+void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *jobs, const int32_t *n_jobs, int cap_jobs, int max_len1,
+                 dartgpu_kmer_hit *out, KmerScratch &S, BatchCtl *ctl, int64_t cap_recs, cudaStream_t st)
 {
-    if (n_jobs <= 0) return;
+    if (cap_jobs <= 0) return;
+    const int sms = sm_count();
     const int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
-    S.ntiles.reserve(n_jobs + 2); S.cap.reserve(n_jobs + 2); S.count.reserve(n_jobs + 2);
-    S.tile_off.reserve(n_jobs + 2); S.rec_off.reserve(n_jobs + 2);
-    S.heavy_list.reserve(n_jobs + 2); S.heavy_count.reserve(4); S.h_total.reserve(2);
-    const size_t tmp = scan_tmp_bytes(n_jobs);
+    S.ntiles.reserve(cap_jobs + 2); S.cap.reserve(cap_jobs + 2); S.count.reserve(cap_jobs + 2);
+    S.tile_off.reserve(cap_jobs + 2); S.rec_off.reserve(cap_jobs + 2);
+    S.heavy_list.reserve(cap_jobs + 2); S.heavy_count.reserve(4);
+    S.recs.reserve((size_t)cap_recs + 1);
+    const size_t tmp = scan_tmp_bytes(cap_jobs);
     S.scan_tmp.reserve(tmp + 256);
     DG_CUDA(cudaMemsetAsync(S.heavy_count.p, 0, sizeof(uint32_t), st));
-    int g1 = (n_jobs + 1 + 255) / 256; if (g1 > 148 * 8) g1 = 148 * 8;
+    int g1 = (cap_jobs + 1 + 255) / 256; if (g1 > sms * 8) g1 = sms * 8;
     const uint32_t cap_max = getenv("DARTGPU_KMER_CAP") ? (uint32_t)atoi(getenv("DARTGPU_KMER_CAP")) : KS_CAP_MAX;
-    k_kmer_prep<<<g1, 256, 0, st>>>(codes, jobs, n_jobs, tab_cap, cap_max, S.ntiles.p, S.cap.p, S.count.p, S.heavy_list.p, S.heavy_count.p, out);
-    launch_scan_u32_to_i64(S.ntiles.p, S.tile_off.p, n_jobs, S.scan_tmp.p, tmp, st);
-    launch_scan_u32_to_i64(S.cap.p, S.rec_off.p, n_jobs, S.scan_tmp.p, tmp, st);
-    small_d2h(S.h_total.p, S.rec_off.p + n_jobs, sizeof(int64_t), st);
-    DG_CUDA(dg_stream_sync(st));
-    S.recs.reserve((size_t)S.h_total.p[0] + 1);
-    k_kmer_scan<<<148 * 8, KS_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, S.tile_off.p, S.rec_off.p, S.cap.p, S.count.p, S.recs.p);
-    k_kmer_walk<<<n_jobs < 148 * 16 ? n_jobs : 148 * 16, 128, 0, st>>>(jobs, n_jobs, S.rec_off.p, S.cap.p, S.count.p, S.recs.p,
-                                                                      S.heavy_list.p, S.heavy_count.p, out);
+    k_kmer_prep<<<g1, 256, 0, st>>>(codes, jobs, n_jobs, cap_jobs, tab_cap, cap_max, S.ntiles.p, S.cap.p, S.count.p, S.heavy_list.p,
+                                    S.heavy_count.p, ctl, out);
+    launch_scan_u32_to_i64(S.ntiles.p, S.tile_off.p, cap_jobs, S.scan_tmp.p, tmp, st);
+    launch_scan_u32_to_i64(S.cap.p, S.rec_off.p, cap_jobs, S.scan_tmp.p, tmp, st);
+    launch_ctl_check(ctl, &ctl->kmer_recs, S.rec_off.p + cap_jobs, cap_recs, CAP_KRECS, st);
+    k_kmer_scan<<<sms * 8, KS_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, cap_jobs, S.tile_off.p, S.rec_off.p, S.cap.p, S.count.p, S.recs.p, ctl);
+    k_kmer_walk<<<cap_jobs < sms * 16 ? cap_jobs : sms * 16, 128, 0, st>>>(jobs, n_jobs, cap_jobs, S.rec_off.p, S.cap.p, S.count.p, S.recs.p,
+                                                                          S.heavy_list.p, S.heavy_count.p, ctl, out);
     // whatever the fast path declined: the ring kernel, reading the list's length on the device
     const int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
     const size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8 + 2048) * 4;
     if (smem > 48 * 1024) {          // the opt-in is per device and cheap: set it on the device this launch goes to
         DG_CUDA(cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int grid = n_jobs < 148 * 4 ? n_jobs : 148 * 4;
-    k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, S.heavy_list.p, S.heavy_count.p, tab_cap, ring, out);
+    const int grid = cap_jobs < sms * 4 ? cap_jobs : sms * 4;
+    k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, S.heavy_list.p, S.heavy_count.p, tab_cap, ring, ctl, out);
 }
 
 } // namespace dartgpu

@@ -17,7 +17,7 @@
 //                base is handed down the lanes systolically: 3 shuffles per 4 cells.  Two traceback bits per cell go to
 //                global scratch, 16 cells per word, and are walked back by the whole warp (32 rows of flag words in
 //                registers, handed round by shuffle).  Integer pipes only.
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 
 #include "dartgpu_internal.h"
 
@@ -38,16 +38,17 @@ __device__ __forceinline__ bool nw_thread_class(int m, int n);
 
 __global__ void __launch_bounds__(NW_THREADS)
 k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, const uint32_t *__restrict__ order,
-     const uint32_t *__restrict__ sorted_keys, int n_jobs,
+     const BatchCtl *__restrict__ ctl, int round, int cap_jobs,
      uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops)
 {
+    if (ctl->abort) return;
+    const int n_jobs = min(ctl->nw_jobs[round], cap_jobs);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     int32_t *rb = rowbuf + (size_t)warp * rowbuf_per_warp;
-    // the jobs k_nw_thread does not take are the tail of the shape-sorted list (key 0xFFFF)
-    int first = 0;
-    { int lo = 0, hi = n_jobs; while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted_keys[mid] < 0xFFFFu) lo = mid + 1; else hi = mid; } first = lo; }
+    // the jobs k_nw_thread does not take are the tail of the shape-sorted list (the last bin)
+    const int first = ctl->nw_small[round];
 
     for (int k = first + warp; k < n_jobs; k += nwarps) {
         const int job = (int)order[k];
@@ -57,6 +58,10 @@ k_nw(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict_
             const int cnt = max(m, 0) + max(n, 0);
             for (int t = lane; t < cnt; t += 32) ops[J.op_off + t] = (uint8_t)(m <= 0 ? 1 : 2);
             if (lane == 0) nops[job] = cnt;
+            continue;
+        }
+        if (m > 32 * NW_ROWS && (size_t)2 * (n + 1) > rowbuf_per_warp) {   // cannot happen: the host sizes the row buffer from the bound on n
+            if (lane == 0) { nops[job] = 0; atomicOr(const_cast<int32_t *>(&ctl->err), ERR_NW_WIDTH); }
             continue;
         }
         const int wpr = (n + 15) >> 4;
@@ -171,21 +176,109 @@ constexpr int NWT_THREADS = 128, NWT_MAX = 64;
 constexpr int NWT_NEG = -30000;
 __device__ __forceinline__ bool nw_thread_class(int m, int n) { return m >= 1 && n >= 1 && m <= NWT_MAX && n <= NWT_MAX; }
 
-__global__ void k_nw_sort_keys(const NwJobDev *__restrict__ jobs, int n_jobs, uint32_t *keys, uint32_t *vals)
+// ---- shape-class counting sort of the job queue (replaces round 1's cub radix sort + 3 scans + 4 host read-backs) ----
+// bin = (n-1)*64 + (m-1) for the thread-per-alignment class, NW_BINS-1 for everything else.  k_nw_prepare also hands every
+// job its slices of the column / traceback-flag / Rvec-Lvec pools (one atomic per CTA and pool: slice order is arbitrary and
+// nothing depends on it) and accumulates the work counters.
+__device__ __forceinline__ int nw_bin(int m, int n) { return nw_thread_class(m, n) ? (n - 1) * NWT_MAX + (m - 1) : NW_BINS - 1; }
+
+__global__ void __launch_bounds__(256)
+k_nw_prepare(NwJobDev *__restrict__ jobs, int cap_jobs, int round, int with_aux, uint32_t *__restrict__ hist, BatchCtl *ctl)
 {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
-        const int m = jobs[j].m, n = jobs[j].n;
-        keys[j] = nw_thread_class(m, n) ? (uint32_t)(n << 7 | m) : 0xFFFFu;
-        vals[j] = (uint32_t)j;
+    if (ctl->abort) return;
+    typedef cub::BlockScan<unsigned int, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ unsigned long long s_base[3];
+    const int n_jobs = min(ctl->nw_jobs[round], cap_jobs);
+    unsigned long long cells = 0;
+    int mx = 0;
+    for (int j0 = blockIdx.x * 256; j0 < n_jobs; j0 += gridDim.x * 256) {
+        const int j = j0 + threadIdx.x;
+        unsigned int so = 0, sf = 0, sa = 0;
+        int m = 0, n = 0;
+        if (j < n_jobs) {
+            m = jobs[j].m; n = jobs[j].n;
+            so = (unsigned)(max(m, 0) + max(n, 0));
+            sf = (m > 0 && n > 0) ? (unsigned)(m * ((n + 15) >> 4)) : 0u;
+            sa = (with_aux && !(j & 1)) ? (unsigned)(2 * (max(m, 0) + 1)) : 0u;
+            atomicAdd(&hist[nw_bin(m, n)], 1u);
+            if (m > 0 && n > 0) cells += (unsigned long long)m * n;
+            mx = max(mx, n);
+        }
+        unsigned int po, pf, pa, to, tf, ta;
+        Scan(tmp).ExclusiveSum(so, po, to); __syncthreads();
+        Scan(tmp).ExclusiveSum(sf, pf, tf); __syncthreads();
+        Scan(tmp).ExclusiveSum(sa, pa, ta); __syncthreads();
+        if (threadIdx.x == 0) {
+            s_base[0] = atomicAdd(&ctl->nw_ops[round], (unsigned long long)to);
+            s_base[1] = atomicAdd(&ctl->nw_flags[round], (unsigned long long)tf);
+            s_base[2] = ta ? atomicAdd(&ctl->nw_aux[round], (unsigned long long)ta) : 0ull;
+        }
+        __syncthreads();
+        if (j < n_jobs) { jobs[j].op_off = (int64_t)(s_base[0] + po); jobs[j].flag_off = (int64_t)(s_base[1] + pf); jobs[j].aux_off = (int64_t)(s_base[2] + pa); }
+        __syncthreads();
+    }
+    mx = __reduce_max_sync(FULLM, mx);
+    for (int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(FULLM, cells, d);
+    if ((threadIdx.x & 31) == 0) {
+        if (mx > 0) atomicMax(&ctl->nw_max_n[round], mx);
+        if (cells) atomicAdd(&ctl->work[0], cells);
+    }
+}
+
+// one CTA: exclusive scan of the histogram; the capacity check of the three pools
+__global__ void __launch_bounds__(1024)
+k_nw_bins(const uint32_t *__restrict__ hist, uint32_t *__restrict__ bin_start, uint32_t *__restrict__ bin_cur, int round,
+          long long cap_ops, long long cap_flags, long long cap_aux, BatchCtl *ctl)
+{
+    if (ctl->abort) return;
+    typedef cub::BlockScan<unsigned int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    constexpr int PER = (NW_BINS + 1023) / 1024;        // 5 consecutive bins per thread
+    unsigned int v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { const int b = threadIdx.x * PER + i; v[i] = b < NW_BINS ? hist[b] : 0u; sum += v[i]; }
+    unsigned int pre;
+    Scan(tmp).ExclusiveSum(sum, pre);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int b = threadIdx.x * PER + i;
+        if (b < NW_BINS) { bin_start[b] = pre; bin_cur[b] = pre; if (b == NW_BINS - 1) ctl->nw_small[round] = (int32_t)pre; }
+        pre += v[i];
+    }
+    if (threadIdx.x == 0 && ((long long)ctl->nw_ops[round] > cap_ops || (long long)ctl->nw_flags[round] > cap_flags || (long long)ctl->nw_aux[round] > cap_aux))
+        atomicOr(&ctl->abort, round == 0 ? CAP_NW_B : CAP_NW_C);
+}
+
+// order[] = job ids grouped by bin; the lanes of a warp that hold jobs of the same bin share one atomic
+__global__ void __launch_bounds__(256)
+k_nw_scatter(const NwJobDev *__restrict__ jobs, int cap_jobs, int round, uint32_t *__restrict__ bin_cur, uint32_t *__restrict__ order,
+             const BatchCtl *__restrict__ ctl)
+{
+    if (ctl->abort) return;
+    const int n_jobs = min(ctl->nw_jobs[round], cap_jobs);
+    const int lane = threadIdx.x & 31;
+    for (int j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; j0 < n_jobs; j0 += gridDim.x * blockDim.x) {
+        const int j = j0 + lane;
+        const bool valid = j < n_jobs;
+        const int bin = valid ? nw_bin(jobs[j].m, jobs[j].n) : -1 - lane;
+        const unsigned peers = __match_any_sync(FULLM, bin);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (valid && lane == leader) base = atomicAdd(&bin_cur[bin], (unsigned)__popc(peers));
+        base = __shfl_sync(FULLM, base, leader);
+        if (valid) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)j;
     }
 }
 
 __global__ void __launch_bounds__(NWT_THREADS)
 k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, const uint32_t *__restrict__ order,
-            const uint32_t *__restrict__ sorted_keys, int n_jobs, uint32_t *next_chunk, uint32_t *flags, uint8_t *ops, int32_t *nops)
+            const BatchCtl *__restrict__ ctl, int round, uint32_t *next_chunk, uint32_t *flags, uint8_t *ops, int32_t *nops)
 {
+    if (ctl->abort) return;
     __shared__ int16_t sS[NWT_MAX + 1][NWT_THREADS], sT[NWT_MAX + 1][NWT_THREADS];
     const int tid = threadIdx.x;
+    const int n_jobs = ctl->nw_small[round];              // the shape-sorted jobs of this class come first
     const int n_chunks = (n_jobs + 31) / 32;
     // chunks of 32 shape-sorted jobs are handed out dynamically to the WARPS, the largest shapes first, so that the grid
     // finishes together (with a static stride the CTAs that drew the chunks of 60 x 60 jobs ran long after the others on
@@ -196,7 +289,7 @@ k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__re
         chunk = __shfl_sync(FULLM, chunk, 0);
         if (chunk >= n_chunks) break;
         const int k = (n_chunks - 1 - chunk) * 32 + (tid & 31);
-        if (k >= n_jobs || sorted_keys[k] == 0xFFFFu) continue;       // sorted: warp-class jobs are at the end
+        if (k >= n_jobs) continue;
         const int job = (int)order[k];
         const NwJobDev J = jobs[job];
         const int m = J.m, n = J.n;
@@ -271,7 +364,7 @@ __global__ void __launch_bounds__(256) k_int32_peak(int *out, int iters, int see
 
 double measure_int32_ops_per_second(cudaStream_t st)
 {
-    const int grid = 148 * 8, iters = 1 << 14;
+    const int grid = sm_count() * 8, iters = 1 << 14;
     DevBuf<int> out;
     out.reserve((size_t)grid * 256);
     cudaEvent_t e0, e1;
@@ -291,29 +384,72 @@ double measure_int32_ops_per_second(cudaStream_t st)
     return (double)grid * 256 * iters * 16.0 / (best * 1e-3);            // 8 adds + 8 max per iteration
 }
 
-int nw_grid_warps() { return 148 * 8 * (NW_THREADS / 32); }
-
-void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwJobDev *jobs, int n_jobs,
-               uint32_t *flags, int32_t *rowbuf, size_t rowbuf_per_warp, uint8_t *ops, int32_t *nops, NwScratch &S, cudaStream_t st)
+// ---- L2 gather microbenchmark: the roof of k_search on an L2-resident index ("L2 and INT32 peaks must be
+// measured the same way by a microbenchmark on the box").  Every thread issues independent 32-byte (one sector) loads at
+// pseudo-random block addresses of a table that fits L2 -- the access pattern of a rank query (seed_kernels.cu load_block).
+__global__ void __launch_bounds__(256) k_l2_gather(const uint4 *__restrict__ table, uint32_t n_blocks_mask, int iters, uint32_t *out)
 {
-    if (n_jobs <= 0) return;
-    // thread-per-job class, sorted by shape
-    S.keys.reserve(n_jobs); S.vals.reserve(n_jobs); S.keys2.reserve(n_jobs); S.vals2.reserve(n_jobs);
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, S.keys.p, S.keys2.p, S.vals.p, S.vals2.p, n_jobs, 0, 16, st);
-    S.tmp.reserve(tmp + 256);
-    int g0 = (n_jobs + 255) / 256; if (g0 > 148 * 8) g0 = 148 * 8;
-    k_nw_sort_keys<<<g0, 256, 0, st>>>(jobs, n_jobs, S.keys.p, S.vals.p);
-    tmp = S.tmp.cap;
-    cub::DeviceRadixSort::SortPairs(S.tmp.p, tmp, S.keys.p, S.keys2.p, S.vals.p, S.vals2.p, n_jobs, 0, 16, st);
-    int gt = (n_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > 148 * 6) gt = 148 * 6;
-    S.counter.reserve(4);
-    cudaMemsetAsync(S.counter.p, 0, sizeof(uint32_t), st);
-    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, jobs, S.vals2.p, S.keys2.p, n_jobs, S.counter.p, flags, ops, nops);
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {            // 8 independent sector loads in flight per thread
+            x = x * 1664525u + 1013904223u;
+            const uint32_t blk = (x >> 7) & n_blocks_mask;
+            uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                         : "l"(reinterpret_cast<const char *>(table) + (size_t)blk * 32));
+            acc += r0 ^ r7;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+double measure_l2_gather_bytes_per_second(cudaStream_t st, size_t table_bytes)
+{
+    size_t blocks = 1;
+    while (blocks * 2 * 32 <= table_bytes) blocks <<= 1;          // power of two, <= table_bytes
+    const int grid = sm_count() * 8, iters = 512;
+    DevBuf<uint4> table; DevBuf<uint32_t> out;
+    table.reserve(blocks * 2); out.reserve((size_t)grid * 256);
+    DG_CUDA(cudaMemsetAsync(table.p, 1, blocks * 32, st));
+    cudaEvent_t e0, e1;
+    DG_CUDA(cudaEventCreate(&e0)); DG_CUDA(cudaEventCreate(&e1));
+    k_l2_gather<<<grid, 256, 0, st>>>(table.p, (uint32_t)(blocks - 1), iters, out.p);     // warm-up: pulls the table into L2
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        DG_CUDA(cudaEventRecord(e0, st));
+        k_l2_gather<<<grid, 256, 0, st>>>(table.p, (uint32_t)(blocks - 1), iters, out.p);
+        DG_CUDA(cudaEventRecord(e1, st));
+        DG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        DG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return (double)grid * 256 * iters * 8 * 32.0 / (best * 1e-3);
+}
+
+int nw_grid_warps() { return sm_count() * 8 * (NW_THREADS / 32); }
+
+void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwRound &R, BatchCtl *ctl, NwScratch &S, cudaStream_t st)
+{
+    if (R.cap_jobs <= 0) return;
+    const int sms = sm_count();
+    S.hist.reserve(NW_BINS + 1); S.bin_start.reserve(NW_BINS + 1); S.bin_cur.reserve(NW_BINS + 1); S.order.reserve(R.cap_jobs); S.counter.reserve(4);
+    DG_CUDA(cudaMemsetAsync(S.hist.p, 0, (NW_BINS + 1) * sizeof(uint32_t), st));
+    DG_CUDA(cudaMemsetAsync(S.counter.p, 0, sizeof(uint32_t), st));
+    int g0 = (R.cap_jobs + 255) / 256; if (g0 > sms * 8) g0 = sms * 8;
+    k_nw_prepare<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, R.with_aux, S.hist.p, ctl);
+    k_nw_bins<<<1, 1024, 0, st>>>(S.hist.p, S.bin_start.p, S.bin_cur.p, R.round, R.cap_ops, R.cap_flags, R.cap_aux, ctl);
+    k_nw_scatter<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, S.bin_cur.p, S.order.p, ctl);
+    int gt = (R.cap_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > sms * 6) gt = sms * 6;
+    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, R.jobs, S.order.p, ctl, R.round, S.counter.p, R.flags, R.ops, R.nops);
     // everything larger: a warp per job
-    int want = (n_jobs + (NW_THREADS / 32) - 1) / (NW_THREADS / 32);
-    int grid = want < 148 * 8 ? want : 148 * 8;
-    k_nw<<<grid, NW_THREADS, 0, st>>>(ix, codes, jobs, S.vals2.p, S.keys2.p, n_jobs, flags, rowbuf, rowbuf_per_warp, ops, nops);
+    int want = (R.cap_jobs + (NW_THREADS / 32) - 1) / (NW_THREADS / 32);
+    int grid = want < sms * 8 ? want : sms * 8;
+    k_nw<<<grid, NW_THREADS, 0, st>>>(ix, codes, R.jobs, S.order.p, ctl, R.round, R.cap_jobs, R.flags, R.rowbuf, R.rowbuf_per_warp, R.ops, R.nops);
 }
 
 } // namespace dartgpu

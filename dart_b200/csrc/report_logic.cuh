@@ -45,7 +45,7 @@ struct CandState {        // AlignmentCandidate_t + AlignmentReport_t of one can
     int64_t cig_off;      // slice of the CIGAR pair pool
     int64_t text_off;     // CIGAR text
     int32_t read;
-    int32_t seed_begin, seed_count;   // run inside the read's sorted seed keys (absolute index)
+    int32_t seed_begin, seed_count;   // run inside the read's sorted seed keys, relative to the read's first seed (Env::seed_off)
     int32_t Score, PairedIdx, SJtype;
     int32_t sv_n, sv_cap;
     int32_t cig_cap, cig_n, text_len;
@@ -120,7 +120,8 @@ struct Env {
     const int64_t *ends; const int32_t *end_chr; int n_ends;   // sorted ChrLocMap
     const int64_t *chr_fwd;                                     // ChromosomeVec[i].FowardLocation
     const uint8_t *codes; const int64_t *code_off; const int32_t *rlen;
-    const uint64_t *keys;
+    const uint64_t *keys; const int64_t *seed_off;              // sorted seed keys of the batch; first seed of every read
+    BatchCtl *ctl;                                              // device kernels only: counts / abort / error flags of the batch
     CandState *cs; RSeed *pool;
     // job queues
     KmerJobDev *kjobs; int32_t *kjob_count; const dartgpu_kmer_hit *khits;
@@ -296,7 +297,7 @@ HDN void phase_a(const Env &E, CandState &c, RSeed *sv)
     if (!c.live) return;
     int32_t n = c.seed_count;
     for (int s = 0; s < n; s++) {
-        uint64_t key = E.keys[c.seed_begin + s];
+        uint64_t key = E.keys[E.seed_off[c.read] + c.seed_begin + s];
         RSeed &d = sv[s];
         d.gPos = key_gpos(key); d.rPos = key_rpos(key); d.rLen = d.gLen = key_len(key);
         d.PosDiff = d.gPos - d.rPos; d.simple = 1; d.acceptor = 0; d.job = -1; d.pad0 = d.pad1 = 0; d.pad2 = 0;

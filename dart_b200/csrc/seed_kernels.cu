@@ -25,6 +25,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "dartgpu_internal.h"
@@ -117,7 +118,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     int64_t wbase = 0;
     uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0, kidx = 0;
     IdxT x1 = 0;
-    uint32_t st_steps = 0, st_splits = 0;
+    uint32_t st_steps = 0, st_splits = 0, st_loads = 0;
 
     // next search start of the current read: skip ambiguous bases, then either a table lookup (JUMP) or the reference's
     // single-base start (STEP); NEED when the read has no start left (IdentifySeedPairs' `pos < rlen - 13`)
@@ -198,6 +199,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                 const OccBlock B0 = load_block(addr0, 0);
                 OccBlock B1 = B0;
                 if (two) B1 = load_block(addr1, 0);
+                st_loads += two ? 2u : 1u;                                // 32-byte sectors really requested (L2 roofline)
                 if (stepping) {
                     const uint32_t ok = block_rank(B0, (uint32_t)kk & 63u, c), ol = block_rank(B1, (uint32_t)ll & 63u, c);
                     st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
@@ -226,30 +228,38 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     }
     if (have_read) { a.nrec[r] = nr; a.nhits[r] = nh; }
     __syncwarp();
-    const unsigned long long ws = warp_sum(st_steps), wp = warp_sum(st_splits);
+    const unsigned long long ws = warp_sum(st_steps), wp = warp_sum(st_splits), wl = warp_sum(st_loads);
     if ((threadIdx.x & 31) == 0 && ws) {
         atomicAdd(&a.stats->ext_steps, ws);
         atomicAdd(&a.stats->ext_blocks, ws + wp);
+        atomicAdd(&a.stats->sector_loads, wl);
     }
 }
 
 static bool fits32(const DevIndex &ix) { return !ix.sa_wide; }
 
+// occupancy of the two instantiations, per device (a process drives several GPUs from several host threads)
+struct SearchCfg { std::atomic<int> occ32{0}, occ64{0}; };
+static SearchCfg g_search_cfg[64];
+
 void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
 {
     if (a.n_reads <= 0) return;
     // exactly one wave: as many CTAs as are resident at once (a partial second wave would idle most SMs at the end)
-    static int occ32 = 0, occ64 = 0, sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SearchCfg &cfg = g_search_cfg[dev >= 0 && dev < 64 ? dev : 0];
+    int occ32 = cfg.occ32.load(std::memory_order_acquire), occ64 = cfg.occ64.load(std::memory_order_acquire);
+    if (!occ32 || !occ64) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k_search<uint32_t>, SEARCH_THREADS, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_search<uint64_t>, SEARCH_THREADS, 0);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        occ32 = std::max(1, occ32); occ64 = std::max(1, occ64);
+        cfg.occ32.store(occ32, std::memory_order_release); cfg.occ64.store(occ64, std::memory_order_release);
     }
+    const int sms = sm_count();
     const bool narrow = fits32(ix);
     int want = (a.n_reads + SEARCH_THREADS - 1) / SEARCH_THREADS;
-    int grid = sms * std::max(1, narrow ? occ32 : occ64);
+    int grid = sms * (narrow ? occ32 : occ64);
     if (want < grid) grid = want;
     // 3/4 of the batch is split statically between the CTAs, the last quarter is stolen read by read
     const int per_cta = (int)((int64_t)a.n_reads * 3 / 4 / grid);
@@ -292,6 +302,7 @@ void launch_scan_hits(const SeedLaunch &a, void *tmp, size_t tmp_bytes, cudaStre
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_expand(SeedLaunch a)
 {
+    if (a.ctl->abort) return;
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     for (; r < a.n_reads; r += gridDim.x * blockDim.x) {
         int64_t o = a.seed_off[r];
@@ -312,8 +323,10 @@ __global__ void k_expand(SeedLaunch a)
 // iteration, a lane picks up its next hit the moment it finishes one so the warp stays busy.
 template <typename IdxT, typename SaT>
 __global__ void __launch_bounds__(256)
-k_locate(DevIndex ix, SeedLaunch a, int64_t total)
+k_locate(DevIndex ix, SeedLaunch a)
 {
+    if (a.ctl->abort) return;
+    const int64_t total = a.ctl->total_seeds;
     __shared__ uint64_t s_L2[5];
     if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
     __syncthreads();
@@ -363,16 +376,16 @@ k_locate(DevIndex ix, SeedLaunch a, int64_t total)
     }
 }
 
-void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, int64_t total, cudaStream_t st)
+void launch_expand_locate(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
 {
-    if (a.n_reads <= 0 || total <= 0) return;
+    if (a.n_reads <= 0) return;
+    const int cap = sm_count() * 8;
     int grid = (a.n_reads + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > cap) grid = cap;
     k_expand<<<grid, 256, 0, st>>>(a);
-    int64_t want = (total + 255) / 256;
-    int g2 = (int)(want < 148 * 8 ? want : 148 * 8);
-    if (ix.sa_wide) k_locate<uint64_t, uint64_t><<<g2, 256, 0, st>>>(ix, a, total);   // sa_wide <=> 64-bit intervals
-    else k_locate<uint32_t, uint32_t><<<g2, 256, 0, st>>>(ix, a, total);
+    // the hit count lives on the device (a.ctl->total_seeds): a full grid, threads beyond the count leave at once
+    if (ix.sa_wide) k_locate<uint64_t, uint64_t><<<cap, 256, 0, st>>>(ix, a);   // sa_wide <=> 64-bit intervals
+    else k_locate<uint32_t, uint32_t><<<cap, 256, 0, st>>>(ix, a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -456,6 +469,7 @@ __device__ __forceinline__ void sort_cluster_group(const DevIndex &ix, const See
 __global__ void __launch_bounds__(256)
 k_sort_cluster_small(DevIndex ix, SeedLaunch a)
 {
+    if (a.ctl->abort) return;
     const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & ~7;
     const unsigned gmask = 0xFFu << gshift;
     const int ngroups = (gridDim.x * blockDim.x) >> 3;
@@ -478,6 +492,7 @@ k_sort_cluster_small(DevIndex ix, SeedLaunch a)
 __global__ void __launch_bounds__(256)
 k_sort_cluster_warp(DevIndex ix, SeedLaunch a)
 {
+    if (a.ctl->abort) return;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nmid = *a.mid_count;
@@ -493,6 +508,7 @@ constexpr int BIG_SM_CAP = 4096; // keys sorted in shared memory up to this many
 __global__ void __launch_bounds__(256)
 k_sort_cluster_big(DevIndex ix, SeedLaunch a)
 {
+    if (a.ctl->abort) return;
     __shared__ uint64_t sm[BIG_SM_CAP];
     const int tid = threadIdx.x;
     const uint32_t nbig = *a.big_count;
@@ -504,7 +520,7 @@ k_sort_cluster_big(DevIndex ix, SeedLaunch a)
         while (N < n) N <<= 1;
         uint64_t *buf = sm;
         if (N > BIG_SM_CAP) {
-            if ((size_t)N > a.big_scratch_per_cta) { if (tid == 0) a.ncand[r] = 0xFFFFFFFFu; continue; } // cannot happen: bound = cap_rec*max_dup
+            if ((size_t)N > a.big_scratch_per_cta) { if (tid == 0) { a.ncand[r] = 0; atomicOr(&a.ctl->err, ERR_SORT_SCRATCH); } continue; } // cannot happen: bound = cap_rec*max_dup
             buf = a.big_scratch + (size_t)blockIdx.x * a.big_scratch_per_cta;
         }
         for (int64_t i = tid; i < N; i += blockDim.x) buf[i] = i < n ? a.keys[off + i] : ~0ull;
@@ -553,13 +569,14 @@ k_sort_cluster_big(DevIndex ix, SeedLaunch a)
 void launch_sort_cluster(const DevIndex &ix, const SeedLaunch &a, cudaStream_t st)
 {
     if (a.n_reads <= 0) return;
+    const int sms = sm_count();
     cudaMemsetAsync(a.big_count, 0, sizeof(uint32_t), st);
     cudaMemsetAsync(a.mid_count, 0, sizeof(uint32_t), st);
     int64_t want = ((int64_t)a.n_reads * 8 + 255) / 256;
-    int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    int grid = (int)(want < sms * 8 ? want : sms * 8);
     k_sort_cluster_small<<<grid, 256, 0, st>>>(ix, a);
-    k_sort_cluster_warp<<<148 * 4, 256, 0, st>>>(ix, a);
-    k_sort_cluster_big<<<148, 256, 0, st>>>(ix, a);
+    k_sort_cluster_warp<<<sms * 4, 256, 0, st>>>(ix, a);
+    k_sort_cluster_big<<<sms, 256, 0, st>>>(ix, a);
 }
 
 } // namespace dartgpu

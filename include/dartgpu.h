@@ -9,7 +9,10 @@
  * Conventions
  *   - every function returns DARTGPU_OK (0) or a negative DARTGPU_ERR_* code; dartgpu_last_error(ctx)
  *     has the text.  There is NO CPU fallback: without a usable CUDA device every call fails.
- *   - one context per (host thread, GPU).  Contexts on the same device share nothing but the driver.
+ *   - a context = one batch in flight on one GPU: its own CUDA stream, device pools and pinned result buffers.
+ *     Contexts created from the same index on the same device share ONE resident copy of the index tables; a host
+ *     thread may drive several contexts (dartgpu_submit on each, then dartgpu_wait on each) so that the copies and
+ *     kernels of consecutive batches overlap.  A context must not be used from two threads at once.
  *   - result buffers are owned by the context (pinned host memory) and stay valid until the next call
  *     on the same context.
  *   - genome coordinates are the reference's: [0,G) forward strand, [G,2G) reverse complement
@@ -70,8 +73,10 @@ typedef struct {
     const char *const *seq_names; /* bntann1_t.name                                 */
 } dartgpu_index_view;
 
-/* Replaces: the once-per-run index hand-over (src/main.cpp:220-223).  The tables are re-laid-out on the GPU
- * (128-bit-interleaved Occ blocks, 2-bit reference over both strands) and stay resident in HBM. */
+/* Replaces: the once-per-run index hand-over (src/main.cpp:220-223).  The tables are re-laid-out on the GPU (one-sector
+ * Occ32 blocks: 4 x u32 counts + two 64-bit planes per 64 BWT symbols; a densified suffix array; a search-start table;
+ * the 2-bit reference over both strands) and stay resident in HBM, one copy per device.  Texts of 2^33 symbols or more
+ * (genomes over 4.29 Gbp) are rejected with DARTGPU_ERR_INDEX: a seed's coordinate has 33 bits. */
 int  dartgpu_create(dartgpu_ctx **out, int device, const dartgpu_index_view *idx, const dartgpu_params *p);
 /* Convenience: read <prefix>.bwt/.sa/.pac/.ann written by bwt_index / `dart index` / bwa index
  * (formats: src/bwt_index.cpp:15-35, :37-89, :102-121) and call dartgpu_create. */
@@ -188,6 +193,16 @@ typedef struct {
 
 int dartgpu_map_reads(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_map_result *out);
 
+/* The same in two halves, so that ONE host thread keeps several batches in flight per GPU (one per context) — what the
+ * reference does with iThreadNum pthreads pulling chunks under LibraryLock (src/Mapping.cpp:591-595, :792-793).
+ * dartgpu_submit stages the reads (page-locked caller buffers are handed to the DMA engine as they are), enqueues every
+ * kernel of the batch and the copies of the results on the context's stream and returns without waiting for the GPU;
+ * `reads` may be reused as soon as it returns unless it is page-locked (then: after dartgpu_wait).
+ * dartgpu_wait sleeps (no spinning) until the batch is done — the batch's only host synchronisation in steady state —
+ * and hands out the results.  dartgpu_map_reads = submit + wait.  At most one batch per context is in flight. */
+int dartgpu_submit(dartgpu_ctx *ctx, const dartgpu_reads *reads);
+int dartgpu_wait(dartgpu_ctx *ctx, dartgpu_map_result *out);
+
 /* ---- measurement ------------------------------------------------------------------------------------------
  * Device time (CUDA events on the context's stream) and algorithmic work of the kernels launched by the LAST
  * call, for roofline reporting. */
@@ -202,12 +217,16 @@ typedef struct {
     uint64_t nw_jobs, nw_cells;
     uint64_t kmer_jobs, kmer_window_bases, kmer_read_bases;
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t search_sector_loads;     /* 32-byte Occ / start-table sectors the search kernel really requested */
 } dartgpu_stats;
 
 int dartgpu_get_stats(const dartgpu_ctx *ctx, dartgpu_stats *out);
 /* INT32 add/max operations per second of the context's GPU, measured with a saturating microbenchmark: the denominator
  * of the NW kernels' integer roofline. */
 int dartgpu_measure_int32_peak(dartgpu_ctx *ctx, double *ops_per_second);
+/* Bytes per second of independent 32-byte (one sector) gathers at random addresses of a table of `table_bytes` that fits
+ * L2 — the access pattern of a rank query: the roof of the search kernel on an L2-resident index. */
+int dartgpu_measure_l2_peak(dartgpu_ctx *ctx, uint64_t table_bytes, double *bytes_per_second);
 
 /* Device-resident variant of stage 1 for kernel-only timing: upload once, run the seeding kernels many times
  * without any host<->device copy in between (bench.py `value`). */
@@ -215,6 +234,7 @@ int dartgpu_upload_reads(dartgpu_ctx *ctx, const dartgpu_reads *reads);
 int dartgpu_seed_and_cluster_resident(dartgpu_ctx *ctx);   /* results stay on the device */
 /* dartgpu_map_reads over the batch previously uploaded with dartgpu_upload_reads (same `reads`): no read H2D. */
 int dartgpu_map_reads_resident(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_map_result *out);
+int dartgpu_submit_resident(dartgpu_ctx *ctx);            /* dartgpu_submit over the uploaded batch; dartgpu_wait completes it */
 int dartgpu_synchronize(dartgpu_ctx *ctx);
 
 #ifdef __cplusplus

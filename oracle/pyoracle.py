@@ -208,6 +208,8 @@ class Reference:
         L.ref_map_pair.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p,
                                    C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
         L.ref_sequence.restype = C.c_void_p
+        L.ref_hotpath.restype = C.c_double
+        L.ref_hotpath.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
         self._prefix = prefix.encode()  # the library keeps the pointer
         if reload_needed:
             _KEEP.append(self._prefix)
@@ -271,6 +273,14 @@ class Reference:
         out = np.zeros(3, np.int32)
         self.L.ref_gapped_partition(seq, rgaps, l_rpos, l_rlen, l_gpos, l_glen, r_rpos, r_gpos, out)
         return tuple(int(x) for x in out)
+
+    def hotpath(self, bases, offsets, paired: int, threads: int) -> float:
+        """Seconds the reference's per-read functions need for a pre-parsed batch on `threads` threads (no parse / format / IO)."""
+        b = np.ascontiguousarray(bases, np.uint8); o = np.ascontiguousarray(offsets, np.int64)
+        m = C.c_long(0)
+        sec = self.L.ref_hotpath(b.ctypes.data, o.ctypes.data, len(o) - 1, int(paired), int(threads), C.byref(m))
+        self.hotpath_mapped = m.value
+        return float(sec)
 
     def map_single(self, name: bytes, seq: bytes, qual: bytes, sj=None) -> bytes:
         out = C.create_string_buffer(1 << 20)

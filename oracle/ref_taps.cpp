@@ -231,4 +231,77 @@ int ref_map_pair(const char* name1, const char* seq1, int rlen1, const char* qua
 	return n;
 }
 
+// ---- hot-path-only timing (bench.py cpu_baseline_hotpath) -----------------------------------------------
+// The per-read loop body of ReadMapping() (src/Mapping.cpp:600-639) over reads that are ALREADY parsed and
+// encoded in memory, on `threads` pthreads, without OutputPaired/SingledAlignments and without any file IO:
+// the like-for-like CPU denominator of the GPU path's reads/s (the stock binary's wall clock also pays for
+// FASTQ parsing, SAM text and fwrite).  bases = ASCII as ReadItem_t.seq holds them (mate 2 already flipped,
+// src/GetData.cpp:157-168), offsets[n+1].  Returns seconds spent in the parallel region.
 } // extern "C"
+#include <pthread.h>
+#include <time.h>
+namespace {
+struct HotArgs { const char* bases; const int64_t* off; int n; int paired; int tid, nth; long mapped; };
+static void hot_one(ReadItem_t& r, const char* bases, const int64_t* off, int i)
+{
+	memset(&r, 0, sizeof r);
+	r.rlen = (int)(off[i + 1] - off[i]);
+	r.seq = (char*)bases + off[i];
+	r.EncodeSeq = new uint8_t[r.rlen];
+	for (int k = 0; k < r.rlen; k++) r.EncodeSeq[k] = nst_nt4_table[(int)(unsigned char)r.seq[k]];
+}
+static void* hot_worker(void* p)
+{
+	HotArgs* a = (HotArgs*)p;
+	map<pair<int64_t, int64_t>, SpliceJunction_t> sj;
+	const int unit = a->paired ? 2 : 1, units = a->n / unit;
+	const int lo = (int)((int64_t)units * a->tid / a->nth), hi = (int)((int64_t)units * (a->tid + 1) / a->nth);
+	for (int u = lo; u < hi; u++) {
+		if (a->paired) {
+			ReadItem_t r1, r2; hot_one(r1, a->bases, a->off, 2 * u); hot_one(r2, a->bases, a->off, 2 * u + 1);
+			vector<SeedPair_t> s1 = IdentifySeedPairs(r1.rlen, r1.EncodeSeq);
+			vector<AlignmentCandidate_t> a1 = GenerateAlignmentCandidate(r1.rlen, s1);
+			vector<SeedPair_t> s2 = IdentifySeedPairs(r2.rlen, r2.EncodeSeq);
+			vector<AlignmentCandidate_t> a2 = GenerateAlignmentCandidate(r2.rlen, s2);
+			if (CheckPairedAlignmentCandidates(a1, a2)) RemoveUnMatedAlignmentCandidates(a1, a2);
+			RemoveRedundantCandidates(a1); RemoveRedundantCandidates(a2);
+			GenMappingReport(true, r1, a1); GenMappingReport(false, r2, a2);
+			CheckPairedFinalAlignments(r1, r2);
+			SetPairedAlignmentFlag(r1, r2);
+			EvaluateMAPQ(r1); EvaluateMAPQ(r2);
+			if (r1.mapq == 50 || (bFindAllJunction && r1.score > 0)) UpdateLocalSJMap(a1[r1.iBestAlnCanIdx], sj);
+			if (r2.mapq == 50 || (bFindAllJunction && r2.score > 0)) UpdateLocalSJMap(a2[r2.iBestAlnCanIdx], sj);
+			a->mapped += (r1.score > 0) + (r2.score > 0);
+			delete[] r1.EncodeSeq; delete[] r2.EncodeSeq; delete[] r1.AlnReportArr; delete[] r2.AlnReportArr;
+		} else {
+			ReadItem_t r; hot_one(r, a->bases, a->off, u);
+			vector<SeedPair_t> sv = IdentifySeedPairs(r.rlen, r.EncodeSeq);
+			vector<AlignmentCandidate_t> av = GenerateAlignmentCandidate(r.rlen, sv);
+			RemoveRedundantCandidates(av);
+			GenMappingReport(true, r, av);
+			SetSingleAlignmentFlag(r); EvaluateMAPQ(r);
+			if (r.mapq == 50 || (bFindAllJunction && r.score > 0)) UpdateLocalSJMap(av[r.iBestAlnCanIdx], sj);
+			a->mapped += r.score > 0;
+			delete[] r.EncodeSeq; delete[] r.AlnReportArr;
+		}
+	}
+	return 0;
+}
+}
+extern "C" double ref_hotpath(const char* bases, const int64_t* offsets, int n_reads, int paired, int threads, long* mapped)
+{
+	if (threads < 1) threads = 1;
+	vector<HotArgs> args(threads);
+	vector<pthread_t> th(threads);
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int t = 0; t < threads; t++) {
+		args[t] = HotArgs{bases, offsets, n_reads, paired, t, threads, 0};
+		pthread_create(&th[t], NULL, hot_worker, &args[t]);
+	}
+	long m = 0;
+	for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); m += args[t].mapped; }
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	if (mapped) *mapped = m;
+	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}

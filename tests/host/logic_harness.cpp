@@ -96,7 +96,7 @@ int main(int argc, char **argv)
             int nc = or_cluster_read(O, rlen[i], ns, rp.data(), gp.data(), ln.data(), P.max_gaps, P.max_intron, cb.data(), cc.data(), sc.data(), cap);
             for (int k = 0; k < nc; k++) {
                 CandState c{};
-                c.read = i; c.seed_begin = (int32_t)(seed_off[i] + cb[k]); c.seed_count = cc[k]; c.Score = sc[k]; c.PairedIdx = -1; c.SJtype = -1;
+                c.read = i; c.seed_begin = cb[k]; c.seed_count = cc[k]; c.Score = sc[k]; c.PairedIdx = -1; c.SJtype = -1;
                 int64_t pd = gp[cb[k]] - rp[cb[k]]; c.PosDiff = pd < 0 ? 0 : pd;
                 cs.push_back(c);
             }
@@ -121,7 +121,7 @@ int main(int argc, char **argv)
     E.P = PhaseParams{P.max_gaps, P.max_intron, P.min_intron, P.max_mismatch, P.multi_hit, P.pair_end, P.all_sj};
     E.ref = RefView{nullptr, (const uint8_t *)pac.data(), G}; E.G = G;
     E.ends = ends.data(); E.end_chr = end_chr.data(); E.n_ends = (int)ends.size(); E.chr_fwd = fwd.data();
-    E.codes = codes.data(); E.code_off = code_off.data(); E.rlen = rlen.data(); E.keys = keys.data();
+    E.codes = codes.data(); E.code_off = code_off.data(); E.rlen = rlen.data(); E.keys = keys.data(); E.seed_off = seed_off.data();
     E.cs = cs.data(); E.pool = pool.data();
     E.kjobs = kjobs.data(); E.kjob_count = &nk; E.khits = khits.data();
 

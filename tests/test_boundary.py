@@ -83,3 +83,31 @@ def test_samhash_is_order_independent(tmp_path):
     h = lambda p: subprocess.run([exe, str(p)], check=True, capture_output=True, text=True).stdout.split()  # noqa: E731
     assert h(a) == h(b) and h(a)[0] == str(len(lines))
     assert h(c) != h(a)
+
+
+def test_index_wider_than_the_seed_key_is_rejected():
+    """A seed is one 64-bit key with a 33-bit text coordinate (dartgpu_internal.h seed_key): a text of 2^33 symbols or more
+    (genome over 4.29 Gbp) must be refused at index hand-over, not mapped with wrapped coordinates (round-1 advice)."""
+    class View(C.Structure):
+        _fields_ = [("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("bwt_size", C.c_uint64),
+                    ("bwt", C.c_void_p), ("sa_intv", C.c_uint64), ("n_sa", C.c_uint64), ("sa", C.c_void_p),
+                    ("l_pac", C.c_int64), ("pac", C.c_void_p), ("n_seqs", C.c_int32), ("seq_len_arr", C.c_void_p),
+                    ("seq_names", C.c_void_p)]
+    L = capi.load_library()
+    dummy = (C.c_uint64 * 4)()
+    lens = (C.c_int64 * 1)(1 << 32)
+    v = View()
+    v.primary = 1; v.seq_len = 1 << 33; v.l_pac = 1 << 32; v.sa_intv = 32; v.n_sa = 4; v.bwt_size = 4
+    for i in range(5):
+        v.L2[i] = i << 31
+    v.bwt = C.addressof(dummy); v.sa = C.addressof(dummy); v.pac = C.addressof(dummy)
+    v.n_seqs = 1; v.seq_len_arr = C.addressof(lens); v.seq_names = None
+    h = C.c_void_p()
+    L.dartgpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(View), C.c_void_p]
+    rc = L.dartgpu_create(C.byref(h), 0, C.byref(v), None)
+    assert rc == -3 and b"33-bit" in L.dartgpu_last_error(None)
+    v.seq_len = (1 << 33) - 2; v.l_pac = (1 << 32) - 1; lens[0] = v.l_pac    # just inside: fails later (no device / bogus tables), not on the width
+    for i in range(5):
+        v.L2[i] = i * ((v.seq_len) // 4)
+    rc = L.dartgpu_create(C.byref(h), 0, C.byref(v), None)
+    assert b"33-bit" not in L.dartgpu_last_error(None)

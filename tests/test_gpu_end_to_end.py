@@ -108,3 +108,31 @@ def test_full_size_baseline_configs(cfg, n, extra, tmp_path_factory):
     if md5(gs) != md5(rs):
         _compare(gs, rs, gj, rj)          # pinpoints the first differing record
     assert md5(gj) == md5(rj)
+
+
+def test_sharding_over_contexts_and_gpus():
+    """The N-GPU path (contiguous read range per device entry, results merged in input order, junction counts summed by key
+    like UpdateGlobalSJMap, /root/reference/src/Mapping.cpp:567-577, :676-678) over EVERY visible GPU — and, so that the
+    shard / merge code runs on a one-GPU box too, over three contexts of device 0 and over an uneven mix."""
+    import torch
+    w = workload("c5")                              # -m -max_dup 10000 -all_sj: multi-hit reports + junction sums
+    rs, rj = run_reference(w, "dart_canon", 1, (), tag="ref_named")
+    n = torch.cuda.device_count()
+    lists = ["0,0,0", ",".join(str(i) for i in range(n)), ",".join(str(i % n) for i in range(n + 3))]
+    for k, devs in enumerate(lists):
+        gs, gj = _run_gpu(w, (), tag=f"gpu_shard{k}", more=("-devices", devs, "-batch", "300"))
+        _compare(gs, rs, gj, rj)
+    w = workload("c3")
+    rs, rj = run_reference(w, "dart_canon", 1, ("-mis", "5"), tag="ref_mis5")
+    gs, gj = _run_gpu(w, ("-mis", "5"), tag="gpu_shard_c3", more=("-devices", lists[2], "-batch", "500"))
+    _compare(gs, rs, gj, rj)
+
+
+def test_pool_overflow_is_retried_not_truncated(monkeypatch):
+    """Device pools are sized by guesses (the counts only exist on the device): a batch that overflows one must be re-run
+    with a bigger pool and give the very same records.  DARTGPU_CAP_SHRINK makes every first guess 1000x too small."""
+    w = workload("c4")
+    rs, rj = run_reference(w, "dart_canon", 1, (), tag="ref_named")
+    monkeypatch.setenv("DARTGPU_CAP_SHRINK", "1000")
+    gs, gj = _run_gpu(w, (), tag="gpu_shrunk")
+    _compare(gs, rs, gj, rj)
