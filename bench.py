@@ -34,7 +34,8 @@ MIS = os.environ.get("DART_BENCH_MIS")  # None = as BASELINE names the config (n
 # Default = BASELINE config[1] (what `metric` is quoted on at 1 GPU).  DART_BENCH_WORKLOAD=c3 switches to a scaled
 # config[2] (multi-contig genome with gene models, spliced pairs; DART_BENCH_SCALE x 3.1 Gbp) whose Occ table no longer
 # fits L2 — used for the HBM-bound roofline of k_search in profiles/, never for the headline line.
-CONTEXTS = int(os.environ.get("DART_BENCH_CONTEXTS", 4))
+CONTEXTS = int(os.environ.get("DART_BENCH_CONTEXTS", 4))   # batches in flight per GPU (one context each, one host thread for all)
+PARTS = int(os.environ.get("DART_BENCH_PARTS", 2))         # sub-batches a step's batch is cut into
 NW_OPS_PER_CELL = 22   # integer instructions of the recurrence + traceback flags per cell in k_nw_thread's inner loop (SASS listing in profiles/)
 WORKLOAD = os.environ.get("DART_BENCH_WORKLOAD", "c2")
 SCALE = float(os.environ.get("DART_BENCH_SCALE", "0.06"))
@@ -200,43 +201,53 @@ def workload_config(sample_pairs=None):
 
 
 class Lanes:
-    """K contexts of one GPU driven by ONE host thread: submit on each, then wait on each (dartgpu_submit / dartgpu_wait),
-    so K batches are in flight and the copies / kernels of consecutive batches overlap.  The thread sleeps in dartgpu_wait."""
+    """K contexts of one GPU driven by ONE host thread: dartgpu_submit on a context, dartgpu_wait when its next batch is due,
+    so K batches are in flight and the copies / kernels of consecutive batches overlap.  The thread sleeps in dartgpu_wait.
+    A step's batch is cut into PARTS sub-batches; sub-batch j of step s goes to context (s * PARTS + j) mod K."""
 
     def __init__(self, mappers, subs):
-        self.mappers, self.subs = mappers, subs
+        self.mappers, self.subs = mappers, subs          # subs[k] = the sub-batch context k maps (k mod PARTS)
 
     def upload(self):
         for m, sb in zip(self.mappers, self.subs):
             m.upload_reads(sb)
 
     def run(self, resident, steps):
-        """`steps` passes over the batch, the sub-batches round-robin over the contexts; a context is only waited for when
-        its next batch is due (no barrier between steps: that would run the contexts in lockstep)."""
-        busy = [False] * len(self.mappers)
-        for _ in range(steps):
-            for i, (m, sb) in enumerate(zip(self.mappers, self.subs)):
-                if busy[i]:
-                    m.wait(copy=False)
-                m.submit(None if resident else sb)
-                busy[i] = True
-        for i, m in enumerate(self.mappers):
-            if busy[i]:
+        """`steps` passes over the batch.  No barrier between steps: a context is only waited for when it is needed again."""
+        K = len(self.mappers)
+        parts = PARTS
+        busy = [False] * K
+        k = 0
+        for _ in range(steps * parts):
+            m = self.mappers[k]
+            if busy[k]:
                 m.wait(copy=False)
+            m.submit(None if resident else self.subs[k])
+            busy[k] = True
+            k = (k + 1) % K
+        for i in range(K):             # oldest first
+            j = (k + i) % K
+            if busy[j]:
+                self.mappers[j].wait(copy=False)
 
     def stats(self):
+        """Work and event times of one step: the last batch of every context, scaled from K batches to PARTS."""
         sts = [m.stats() for m in self.mappers]
-        return {k: sum(x[k] for x in sts) for k in sts[0]}
+        f = PARTS / len(sts)
+        return {k: sum(x[k] for x in sts) * f for k in sts[0]}
 
 
 def make_lanes(capi, idx, local, params, batch, contexts):
     from dart_b200.shard import shard_bounds
+    assert contexts % PARTS == 0
     mappers = [capi.Mapper(idx, device=local, **params) for _ in range(contexts)]
-    bounds = shard_bounds(batch.n, contexts, True)
-    subs = []
+    bounds = shard_bounds(batch.n, PARTS, True)
+    parts = []
     for a, b in zip(bounds[:-1], bounds[1:]):
         off = batch.offsets[a:b + 1]
-        subs.append(capi.ReadBatch(batch.bases[off[0]:off[-1]].copy(), (off - off[0]).copy()).pin())   # e2e: inputs in pinned host memory
+        parts.append((batch.bases[off[0]:off[-1]], off - off[0]))
+    # every context gets its own page-locked copy of its sub-batch (e2e: inputs in pinned host memory)
+    subs = [capi.ReadBatch(parts[k % PARTS][0].copy(), parts[k % PARTS][1].copy()).pin() for k in range(contexts)]
     return Lanes(mappers, subs)
 
 
@@ -443,7 +454,7 @@ def main():
             "data": "synthetic", "config": workload_config(), "clocks": clocks,
             "e2e": {"value": world * n_reads * args.steps / (ms_e2e * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
-            "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS, "host_threads_per_gpu": 1,
+            "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS, "batches_per_step": PARTS, "host_threads_per_gpu": 1,
             "host_sync": os.environ.get("DARTGPU_SYNC", "block (one sleeping wait per batch)"), "host_cores": os.cpu_count(),
             "roofline": roof,
             "kernels_ms_per_step": {k: st[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h", "ms_host")},

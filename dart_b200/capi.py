@@ -56,7 +56,8 @@ class Stats(C.Structure):
                                            "ms_d2h", "ms_total_device", "ms_host", "ms_report")] +
                 [(n, C.c_uint64) for n in ("kernel_launches", "ext_steps", "ext_blocks", "lf_steps", "hits", "seeds",
                                            "read_bases", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases",
-                                           "kmer_read_bases", "h2d_bytes", "d2h_bytes", "search_sector_loads")])
+                                           "kmer_read_bases", "h2d_bytes", "d2h_bytes", "search_sector_loads")] +
+                [("ms_submit", C.c_double)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -68,7 +68,7 @@ void stats_begin(dartgpu_ctx *c)
 // a fresh control block for the batch (or for its next attempt)
 static void ctl_begin(dartgpu_ctx *c)
 {
-    DG_CUDA(cudaMemsetAsync(c->d_ctl.p, 0, sizeof(BatchCtl), c->stream));
+    launch_zero(c->d_ctl.p, sizeof(BatchCtl), c->stream);
 }
 static void ctl_fetch(dartgpu_ctx *c)      // enqueue the read-back of the control block (a one-warp kernel, not the copy engine)
 {
@@ -227,7 +227,7 @@ void enqueue_seeding(dartgpu_ctx *c)
     c->d_recs.reserve((size_t)n * c->cap_rec);
     c->d_nrec.reserve(n + 1); c->d_nhits.reserve(n + 1); c->d_ncand.reserve(n + 2);
     c->d_seed_off.reserve(n + 2);
-    c->d_big_list.reserve(n + 1); c->d_big_count.reserve(4); c->d_mid_list.reserve(n + 1); c->d_mid_count.reserve(4);
+    c->d_big_list.reserve(n + 1); c->d_mid_list.reserve(n + 1);
     size_t tmp = scan_tmp_bytes(n);
     c->d_scan_tmp.reserve(tmp + 256);
     c->d_keys.reserve(K.seeds + 1); c->d_meta.reserve(K.seeds + 1);
@@ -240,13 +240,12 @@ void enqueue_seeding(dartgpu_ctx *c)
     a.codes = c->d_codes.p; a.dev_off = c->d_dev_off.p; a.rlen = c->d_rlen.p; a.n_reads = n;
     a.cap_rec = c->cap_rec; a.max_dup = c->prm.max_dup; a.max_gaps = c->prm.max_gaps; a.max_intron = c->prm.max_intron;
     a.recs = c->d_recs.p; a.nrec = c->d_nrec.p; a.nhits = c->d_nhits.p; a.seed_off = c->d_seed_off.p;
-    a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = c->d_big_count.p; a.mid_list = c->d_mid_list.p; a.mid_count = c->d_mid_count.p;
-    a.ctl = c->d_ctl.p; a.stats = &c->d_ctl.p->stats; a.packed = c->d_packed.p; a.steal = c->d_steal.p;
+    a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = &c->d_ctl.p->big_count; a.mid_list = c->d_mid_list.p; a.mid_count = &c->d_ctl.p->mid_count;
+    a.ctl = c->d_ctl.p; a.stats = &c->d_ctl.p->stats; a.packed = c->d_packed.p; a.steal = &c->d_ctl.p->steal;
     a.keys = c->d_keys.p; a.meta = c->d_meta.p;
     a.cand_begin = c->d_cand_begin.p; a.cand_count = c->d_cand_count.p; a.cand_score = c->d_cand_score.p;
     a.big_scratch = c->d_big_scratch.p; a.big_scratch_per_cta = per_cta;
 
-    DG_CUDA(cudaMemsetAsync(c->d_nhits.p + n, 0, sizeof(uint32_t), st));
     DG_CUDA(cudaEventRecord(c->ev[2], st));
     launch_search(c->ix, a, st);
     DG_CUDA(cudaGetLastError());
@@ -261,6 +260,37 @@ void enqueue_seeding(dartgpu_ctx *c)
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[6], st));
     c->stats.kernel_launches += 9;
+}
+
+// Several contexts of one device keep several batches in flight so that the copies of one batch overlap the kernels of
+// another.  Left alone, the hardware time-shares the SMs between the streams, the batches advance in lockstep, finish their
+// kernels together and then queue their result copies on the one D2H engine with nothing left to overlap them (measured on
+// config[1], 4 contexts: 7.2 ms per step = kernels + copies, exactly what ONE context needs).  So kernels take turns: the
+// first kernel of the batch submitted as number i on a device waits for the event behind the last kernel of batch i - T
+// (any context of the device).  T = 1 is strict FIFO: no two batches compute at once, copies run under the next batch's
+// kernels.  T = 2 (default) lets two batches share the SMs, half a batch out of phase by construction, so that one fills the
+// launch gaps and small-kernel tails of the other while the convoy still cannot form.  Uploads are not part of a turn.
+// DARTGPU_TURNS=0 switches the mechanism off.
+static const int g_turns = [] { const char *e = getenv("DARTGPU_TURNS"); int v = e ? atoi(e) : 2; return std::max(0, std::min(v, SharedIndex::TURN_RING - 1)); }();
+void compute_turn_begin(dartgpu_ctx *c)
+{
+    if (!g_turns) return;
+    SharedIndex &S = *c->shared;
+    std::lock_guard<std::mutex> lock(S.turn_mutex);
+    if (S.turn_next >= (uint64_t)g_turns) {
+        const int slot = (int)((S.turn_next - g_turns) % SharedIndex::TURN_RING);
+        if (S.turn_ev[slot] && S.turn_owner[slot] != c) DG_CUDA(cudaStreamWaitEvent(c->stream, S.turn_ev[slot], 0));
+    }
+}
+void compute_turn_end(dartgpu_ctx *c)
+{
+    if (!g_turns) return;
+    SharedIndex &S = *c->shared;
+    std::lock_guard<std::mutex> lock(S.turn_mutex);
+    DG_CUDA(cudaEventRecord(c->compute_done, c->stream));
+    const int slot = (int)(S.turn_next % SharedIndex::TURN_RING);
+    S.turn_ev[slot] = c->compute_done; S.turn_owner[slot] = c;
+    S.turn_next++;
 }
 
 // stats of the attempt that went through, from its events and its control block
@@ -649,8 +679,9 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
     c->shared = load_shared_index(c->device, v, c->stream);
     c->ix = c->shared->ix;
     c->G = c->shared->G;
-    c->d_ctl.reserve(1); c->h_ctl.reserve(1); c->d_steal.reserve(4);
+    c->d_ctl.reserve(1); c->h_ctl.reserve(1);
     DG_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventBlockingSync | cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming));
     DG_CUDA(dg_stream_sync(c->stream));
 }
 
@@ -766,6 +797,15 @@ void dartgpu_destroy(dartgpu_ctx *c)
     if (c->in_flight) cudaStreamSynchronize(c->stream);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->done) cudaEventDestroy(c->done);
+    if (c->compute_done) {
+        if (c->shared) {
+            std::lock_guard<std::mutex> lock(c->shared->turn_mutex);
+            for (int i = 0; i < SharedIndex::TURN_RING; i++)
+                if (c->shared->turn_owner[i] == c) { c->shared->turn_ev[i] = nullptr; c->shared->turn_owner[i] = nullptr; }
+        }
+        cudaStreamSynchronize(c->stream);
+        cudaEventDestroy(c->compute_done);
+    }
     if (c->dpipe) free_device_pipe(c->dpipe);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -878,6 +918,7 @@ namespace dartgpu {
 // everything of one attempt behind the (already enqueued or resident) read upload; records the `done` event
 static void enqueue_whole_path(dartgpu_ctx *c)
 {
+    compute_turn_begin(c);
     ctl_begin(c);
     enqueue_seeding(c);
     enqueue_pipeline(c);
@@ -922,6 +963,7 @@ static void wait_batch(dartgpu_ctx *c, dartgpu_map_result *out)
     finish_pipeline(c, out);
     collect_stats(c, true);
     c->stats.ms_host = c->t_submit_ms + t.ms();
+    c->stats.ms_submit = c->t_submit_ms;
 }
 } // namespace dartgpu
 

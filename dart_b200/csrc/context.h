@@ -3,6 +3,7 @@
 #pragma once
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,13 @@ struct SharedIndex {
     DevBuf<KmerStart> d_ktab;       // search-start table
     DevBuf<uint32_t> d_ref2;
     DevBuf<int64_t> d_ends;
+    // Batches of the contexts of this device run their KERNELS in submission order (see compute_turn_begin in capi.cu):
+    // the event behind the kernels of the most recently submitted batch, and the context that owns it.
+    std::mutex turn_mutex;
+    static constexpr int TURN_RING = 8;
+    cudaEvent_t turn_ev[TURN_RING] = {};       // events behind the kernels of the last TURN_RING batches submitted on this device
+    const void *turn_owner[TURN_RING] = {};
+    uint64_t turn_next = 0;                     // batches submitted so far
     ~SharedIndex();
 };
 } // namespace dartgpu
@@ -60,13 +68,12 @@ struct dartgpu_ctx {
     dartgpu::DevBuf<uint32_t> d_padded;
     dartgpu::DevBuf<uint8_t> d_codes;
     dartgpu::DevBuf<uint2> d_packed;         // the search kernel's 2-bit view of the batch
-    dartgpu::DevBuf<uint32_t> d_steal;
     dartgpu::DevBuf<int64_t> d_dev_off;
     dartgpu::DevBuf<int32_t> d_rlen;
 
     // ---- seeding buffers ----
     dartgpu::DevBuf<dartgpu::SearchRec> d_recs;
-    dartgpu::DevBuf<uint32_t> d_nrec, d_nhits, d_ncand, d_meta, d_big_list, d_big_count, d_mid_list, d_mid_count;
+    dartgpu::DevBuf<uint32_t> d_nrec, d_nhits, d_ncand, d_meta, d_big_list, d_mid_list;
     dartgpu::DevBuf<int64_t> d_seed_off;
     dartgpu::DevBuf<uint64_t> d_keys, d_big_scratch;
     dartgpu::DevBuf<int32_t> d_cand_begin, d_cand_count, d_cand_score;
@@ -79,6 +86,7 @@ struct dartgpu_ctx {
     bool in_flight = false, whole_path = false, timed_upload = false;
     int attempts = 0;
     cudaEvent_t done = nullptr;                   // blocking-sync event recorded behind the batch
+    cudaEvent_t compute_done = nullptr;           // recorded behind the batch's last kernel, before its result copies
     double t_submit_ms = 0;
 
     // seeding results on the host
@@ -136,6 +144,9 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
 void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs);
 // the whole per-read path over the uploaded batch: device orchestration, enqueued behind the seeding kernels
 void enqueue_pipeline(dartgpu_ctx *c);
+// Kernels of different contexts of one device take turns (FIFO) instead of time-sharing the SMs: see capi.cu
+void compute_turn_begin(dartgpu_ctx *c);
+void compute_turn_end(dartgpu_ctx *c);
 void finish_pipeline(dartgpu_ctx *c, dartgpu_map_result *out);          // after the batch's synchronisation
 void free_device_pipe(void *p);
 

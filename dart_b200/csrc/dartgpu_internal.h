@@ -84,7 +84,8 @@ struct BatchCtl {
     int32_t nw_max_n[2];
     int32_t abort;                                          // CAP_* bits: a capacity was exceeded, the batch must be re-run
     int32_t err;                                            // ERR_* bits: internal invariants that must never fire
-    int32_t pad;
+    uint32_t steal, big_count, mid_count, heavy_count;    // work-stealing / queue counters of the seeding and 8-mer kernels
+    uint32_t pad;
     unsigned long long work[4];                             // [0] NW cells, [1] 8-mer window bases, [2] 8-mer read bases
     DevStats stats;
 };
@@ -149,6 +150,10 @@ inline cudaError_t dg_stream_sync(cudaStream_t st)
 // index_device.cu
 int sm_count();                                   // SMs of the current device (cached per device, thread-safe)
 void launch_set_i32(int32_t *dst, int32_t v, cudaStream_t st);
+// Zero-fill by a kernel.  Not cudaMemsetAsync: memsets of more than a few KB may be executed by a copy engine, where they
+// queue behind the other contexts' multi-megabyte result copies and stall this context's kernel stream (measured: with
+// two 4 MB memsets per batch no result copy overlapped any kernel, 7.1 ms per step instead of 5.3).
+void launch_zero(void *p, size_t bytes, cudaStream_t st);   // p 4-byte aligned, bytes a multiple of 4
 // dst (a field of *ctl) = *src; sets `bit` in ctl->abort when the value exceeds cap
 void launch_ctl_check(BatchCtl *ctl, long long *dst, const int64_t *src, int64_t cap, int bit, cudaStream_t st);
 void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t st);   // bytes: multiple of 4, pinned destination
@@ -167,7 +172,7 @@ void build_index_files(int device, const uint8_t *pac, int64_t l_pac, const char
 struct SeedLaunch {
     const uint8_t *codes; const int64_t *dev_off; const int32_t *rlen; int n_reads;
     const uint2 *packed;                                        // 16 bases per entry: .x = 2-bit codes (base i at bits 2i), .y = "not ACGT" bits
-    uint32_t *steal; int steal_base; int turn_batch, end_batch;                            // work-stealing counter for the tail of the search kernel
+    uint32_t *steal; int steal_base; int turn_batch, end_batch;                            // work-stealing counter for the tail of the search kernel (in the control block)
     int cap_rec; uint32_t max_dup; int max_gaps, max_intron;
     SearchRec *recs; uint32_t *nrec; uint32_t *nhits;          // search output
     int64_t *seed_off;                                          // n_reads+1, exclusive scan of nhits
@@ -190,7 +195,7 @@ void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, 
 struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int64_t aux_off; int32_t m, n; };
 constexpr int NW_BINS = 64 * 64 + 1;   // shape classes (n, m) of the thread-per-alignment kernel + one for everything larger
 struct NwScratch {         // shape-class counting sort of the job queue, owned by the context
-    DevBuf<uint32_t> hist, bin_start, bin_cur, order, counter;
+    DevBuf<uint32_t> hist, bin_start, bin_cur, order, counter;   // hist and counter are left zeroed by k_nw_bins / the kernels that use them
 };
 struct NwRound {           // one batched NW launch over a job queue whose length lives on the device
     NwJobDev *jobs; const int32_t *n_jobs; int cap_jobs;
@@ -209,7 +214,7 @@ double measure_l2_gather_bytes_per_second(cudaStream_t st, size_t table_bytes);
 // kmer_kernel.cu
 struct KmerJobDev { int64_t s1_off; int64_t gpos; int32_t len1, len2; };
 struct KmerScratch {       // device scratch of the k-mer fast path, owned by the context
-    DevBuf<uint32_t> ntiles, cap, count, recs, heavy_list, heavy_count;
+    DevBuf<uint32_t> ntiles, cap, count, recs, heavy_list;
     DevBuf<int64_t> tile_off, rec_off;
     DevBuf<uint8_t> scan_tmp;
 };

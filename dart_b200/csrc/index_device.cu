@@ -26,6 +26,19 @@ int sm_count()
 __global__ void k_set_i32(int32_t *dst, int32_t v) { *dst = v; }
 void launch_set_i32(int32_t *dst, int32_t v, cudaStream_t st) { k_set_i32<<<1, 1, 0, st>>>(dst, v); }
 
+__global__ void k_zero(uint32_t *p, size_t n_words)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+void launch_zero(void *p, size_t bytes, cudaStream_t st)
+{
+    const size_t n = bytes / 4;
+    if (!n) return;
+    size_t want = (n + 255) / 256;
+    const int cap = sm_count() * 8;
+    k_zero<<<(int)(want < (size_t)cap ? want : (size_t)cap), 256, 0, st>>>(reinterpret_cast<uint32_t *>(p), n);
+}
+
 __global__ void k_ctl_check(BatchCtl *ctl, long long *dst, const int64_t *src, int64_t cap, int bit)
 {
     const long long v = *src;

@@ -412,21 +412,21 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
     const int tab_cap = pow2_at_least(max_len1 < 8 ? 8 : max_len1);
     S.ntiles.reserve(cap_jobs + 2); S.cap.reserve(cap_jobs + 2); S.count.reserve(cap_jobs + 2);
     S.tile_off.reserve(cap_jobs + 2); S.rec_off.reserve(cap_jobs + 2);
-    S.heavy_list.reserve(cap_jobs + 2); S.heavy_count.reserve(4);
+    S.heavy_list.reserve(cap_jobs + 2);
     S.recs.reserve((size_t)cap_recs + 1);
     const size_t tmp = scan_tmp_bytes(cap_jobs);
     S.scan_tmp.reserve(tmp + 256);
-    DG_CUDA(cudaMemsetAsync(S.heavy_count.p, 0, sizeof(uint32_t), st));
+    uint32_t *heavy_count = &ctl->heavy_count;                  // zeroed with the control block
     int g1 = (cap_jobs + 1 + 255) / 256; if (g1 > sms * 8) g1 = sms * 8;
     const uint32_t cap_max = getenv("DARTGPU_KMER_CAP") ? (uint32_t)atoi(getenv("DARTGPU_KMER_CAP")) : KS_CAP_MAX;
     k_kmer_prep<<<g1, 256, 0, st>>>(codes, jobs, n_jobs, cap_jobs, tab_cap, cap_max, S.ntiles.p, S.cap.p, S.count.p, S.heavy_list.p,
-                                    S.heavy_count.p, ctl, out);
+                                    heavy_count, ctl, out);
     launch_scan_u32_to_i64(S.ntiles.p, S.tile_off.p, cap_jobs, S.scan_tmp.p, tmp, st);
     launch_scan_u32_to_i64(S.cap.p, S.rec_off.p, cap_jobs, S.scan_tmp.p, tmp, st);
     launch_ctl_check(ctl, &ctl->kmer_recs, S.rec_off.p + cap_jobs, cap_recs, CAP_KRECS, st);
     k_kmer_scan<<<sms * 8, KS_THREADS, 0, st>>>(ix, codes, jobs, n_jobs, cap_jobs, S.tile_off.p, S.rec_off.p, S.cap.p, S.count.p, S.recs.p, ctl);
     k_kmer_walk<<<cap_jobs < sms * 16 ? cap_jobs : sms * 16, 128, 0, st>>>(jobs, n_jobs, cap_jobs, S.rec_off.p, S.cap.p, S.count.p, S.recs.p,
-                                                                          S.heavy_list.p, S.heavy_count.p, ctl, out);
+                                                                          S.heavy_list.p, heavy_count, ctl, out);
     // whatever the fast path declined: the ring kernel, reading the list's length on the device
     const int ring = pow2_at_least(max_len1 + KMER_TILE + 32);
     const size_t smem = (size_t)(tab_cap + 3 * ring + ring / 32 + 8 + 2048) * 4;
@@ -434,7 +434,7 @@ void launch_kmer(const DevIndex &ix, const uint8_t *codes, const KmerJobDev *job
         DG_CUDA(cudaFuncSetAttribute(k_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int grid = cap_jobs < sms * 4 ? cap_jobs : sms * 4;
-    k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, S.heavy_list.p, S.heavy_count.p, tab_cap, ring, ctl, out);
+    k_kmer<<<grid, KMER_THREADS, smem, st>>>(ix, codes, jobs, S.heavy_list.p, heavy_count, tab_cap, ring, ctl, out);
 }
 
 } // namespace dartgpu

@@ -195,15 +195,19 @@ k_nw_prepare(NwJobDev *__restrict__ jobs, int cap_jobs, int round, int with_aux,
     for (int j0 = blockIdx.x * 256; j0 < n_jobs; j0 += gridDim.x * 256) {
         const int j = j0 + threadIdx.x;
         unsigned int so = 0, sf = 0, sa = 0;
-        int m = 0, n = 0;
+        int m = 0, n = 0, bin = -1 - (int)(threadIdx.x & 31);
         if (j < n_jobs) {
             m = jobs[j].m; n = jobs[j].n;
             so = (unsigned)(max(m, 0) + max(n, 0));
             sf = (m > 0 && n > 0) ? (unsigned)(m * ((n + 15) >> 4)) : 0u;
             sa = (with_aux && !(j & 1)) ? (unsigned)(2 * (max(m, 0) + 1)) : 0u;
-            atomicAdd(&hist[nw_bin(m, n)], 1u);
+            bin = nw_bin(m, n);
             if (m > 0 && n > 0) cells += (unsigned long long)m * n;
             mx = max(mx, n);
+        }
+        {   // histogram: the lanes of a warp that hold the same shape share one atomic (a million single-address atomics otherwise)
+            const unsigned peers = __match_any_sync(FULLM, bin);
+            if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
         }
         unsigned int po, pf, pa, to, tf, ta;
         Scan(tmp).ExclusiveSum(so, po, to); __syncthreads();
@@ -228,16 +232,17 @@ k_nw_prepare(NwJobDev *__restrict__ jobs, int cap_jobs, int round, int with_aux,
 
 // one CTA: exclusive scan of the histogram; the capacity check of the three pools
 __global__ void __launch_bounds__(1024)
-k_nw_bins(const uint32_t *__restrict__ hist, uint32_t *__restrict__ bin_start, uint32_t *__restrict__ bin_cur, int round,
+k_nw_bins(uint32_t *__restrict__ hist, uint32_t *__restrict__ bin_start, uint32_t *__restrict__ bin_cur, uint32_t *__restrict__ next_chunk, int round,
           long long cap_ops, long long cap_flags, long long cap_aux, BatchCtl *ctl)
 {
-    if (ctl->abort) return;
+    if (threadIdx.x == 0) *next_chunk = 0;              // k_nw_thread's hand-out counter
+    // (no early return on abort: the histogram must be left zeroed for the next launch)
     typedef cub::BlockScan<unsigned int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     constexpr int PER = (NW_BINS + 1023) / 1024;        // 5 consecutive bins per thread
     unsigned int v[PER], sum = 0;
 #pragma unroll
-    for (int i = 0; i < PER; i++) { const int b = threadIdx.x * PER + i; v[i] = b < NW_BINS ? hist[b] : 0u; sum += v[i]; }
+    for (int i = 0; i < PER; i++) { const int b = threadIdx.x * PER + i; v[i] = b < NW_BINS ? hist[b] : 0u; sum += v[i]; if (b < NW_BINS) hist[b] = 0u; }
     unsigned int pre;
     Scan(tmp).ExclusiveSum(sum, pre);
 #pragma unroll
@@ -437,12 +442,14 @@ void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwRound &R, Batch
 {
     if (R.cap_jobs <= 0) return;
     const int sms = sm_count();
-    S.hist.reserve(NW_BINS + 1); S.bin_start.reserve(NW_BINS + 1); S.bin_cur.reserve(NW_BINS + 1); S.order.reserve(R.cap_jobs); S.counter.reserve(4);
-    DG_CUDA(cudaMemsetAsync(S.hist.p, 0, (NW_BINS + 1) * sizeof(uint32_t), st));
-    DG_CUDA(cudaMemsetAsync(S.counter.p, 0, sizeof(uint32_t), st));
+    if (!S.hist.p) {                                   // once per context; afterwards k_nw_bins leaves the histogram zeroed
+        S.hist.reserve(NW_BINS + 1); S.counter.reserve(4);
+        launch_zero(S.hist.p, (NW_BINS + 1) * sizeof(uint32_t), st);
+    }
+    S.bin_start.reserve(NW_BINS + 1); S.bin_cur.reserve(NW_BINS + 1); S.order.reserve(R.cap_jobs);
     int g0 = (R.cap_jobs + 255) / 256; if (g0 > sms * 8) g0 = sms * 8;
     k_nw_prepare<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, R.with_aux, S.hist.p, ctl);
-    k_nw_bins<<<1, 1024, 0, st>>>(S.hist.p, S.bin_start.p, S.bin_cur.p, R.round, R.cap_ops, R.cap_flags, R.cap_aux, ctl);
+    k_nw_bins<<<1, 1024, 0, st>>>(S.hist.p, S.bin_start.p, S.bin_cur.p, S.counter.p, R.round, R.cap_ops, R.cap_flags, R.cap_aux, ctl);
     k_nw_scatter<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, S.bin_cur.p, S.order.p, ctl);
     int gt = (R.cap_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > sms * 6) gt = sms * 6;
     k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, R.jobs, S.order.p, ctl, R.round, S.counter.p, R.flags, R.ops, R.nops);

@@ -61,7 +61,7 @@ __global__ void k_cand_init(int n_reads, const int64_t *seed_off, const int64_t 
 
 // candidate pairing / pruning per read (pair), then the seed-pool demand of the survivors (cap[] was zeroed: the prefix sum
 // behind this kernel runs over the candidate table's capacity)
-__global__ void k_pair_prune(int n_units, int paired, const int64_t *cand_off, CandState *cs, uint32_t *cap, const BatchCtl *ctl)
+__global__ void k_pair_prune(int n_units, int paired, const int64_t *cand_off, CandState *cs, uint32_t *cap, int64_t cap_cands, const BatchCtl *ctl)
 {
     if (ctl->abort) return;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
@@ -82,6 +82,8 @@ __global__ void k_pair_prune(int n_units, int paired, const int64_t *cand_off, C
             cap[c] = (uint32_t)k;
         }
     }
+    // zeros behind the candidate count, up to the capacity the prefix sum runs over
+    for (int64_t c = ctl->ncand + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c <= cap_cands; c += (int64_t)gridDim.x * blockDim.x) cap[c] = 0u;
 }
 
 // One thread per candidate.  The candidate's record is worked on in registers and its seeds, when few (the normal
@@ -141,12 +143,12 @@ __global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E,
     }
 }
 
-__global__ void k_cig_caps(const CandState *cs, uint32_t *cap, const BatchCtl *ctl)
+__global__ void k_cig_caps(const CandState *cs, uint32_t *cap, int64_t cap_cands, const BatchCtl *ctl)
 {
     if (ctl->abort) return;
     const int64_t ncand = ctl->ncand;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += (int64_t)gridDim.x * blockDim.x)
-        cap[c] = (cs[c].live && !cs[c].skip) ? (uint32_t)cs[c].cig_cap : 0u;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c <= cap_cands; c += (int64_t)gridDim.x * blockDim.x)
+        cap[c] = (c < ncand && cs[c].live && !cs[c].skip) ? (uint32_t)cs[c].cig_cap : 0u;
 }
 
 // ---- final pass ----
@@ -326,8 +328,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
                                              c->d_cand_score.p, c->d_keys.p, D->cs.p, ctl);
     // ---- pairing / pruning; seed-pool slices of the survivors (prefix sum over the table's capacity, zeros behind the count) ----
     D->u32_a.reserve(cap_c + 2); D->sv_off.reserve(cap_c + 2);
-    DG_CUDA(cudaMemsetAsync(D->u32_a.p, 0, (size_t)(cap_c + 1) * sizeof(uint32_t), st));
-    k_pair_prune<<<grid_for(units), TPB, 0, st>>>(units, paired, D->cand_off.p, D->cs.p, D->u32_a.p, ctl);
+    k_pair_prune<<<grid_for(units), TPB, 0, st>>>(units, paired, D->cand_off.p, D->cs.p, D->u32_a.p, cap_c, ctl);
     scan_u32(c, D, D->u32_a.p, D->sv_off.p, cap_c);
     launch_ctl_check(ctl, &ctl->pool_total, D->sv_off.p + cap_c, K.pool, CAP_POOL, st);
     D->pool.reserve(K.pool + 1);
@@ -347,8 +348,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
     E.kjobs = D->kjobs.p; E.kjob_count = &ctl->nk; E.khits = D->khits.p;
     E.njobs = D->jobsB.p; E.njob_count = &ctl->nw_jobs[0];          // phase B's queue (also used by candidates fast-tracked out of A)
     E.njobs_c = D->jobsC.p; E.njob_count_c = &ctl->nw_jobs[1];      // phase C's queue
-    D->stage.reserve(cap_c + 1);
-    DG_CUDA(cudaMemsetAsync(D->stage.p, 0, (size_t)cap_c + 1, st));
+    D->stage.reserve(cap_c + 1);             // written for every candidate by phase A
     E.stage = D->stage.p;
 
     // ---- phase A -> 8-mer re-seeding ----
@@ -374,8 +374,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
 
     // ---- phase D: CIGAR pairs, score, coordinates ----
     D->cig_off.reserve(cap_c + 2);
-    DG_CUDA(cudaMemsetAsync(D->u32_a.p, 0, (size_t)(cap_c + 1) * sizeof(uint32_t), st));
-    k_cig_caps<<<grid_for(cap_c), TPB, 0, st>>>(D->cs.p, D->u32_a.p, ctl);
+    k_cig_caps<<<grid_for(cap_c + 1), TPB, 0, st>>>(D->cs.p, D->u32_a.p, cap_c, ctl);
     scan_u32(c, D, D->u32_a.p, D->cig_off.p, cap_c);
     launch_ctl_check(ctl, &ctl->cig_total, D->cig_off.p + cap_c, K.cig, CAP_CIG, st);
     D->cig.reserve(K.cig + 1);
@@ -395,6 +394,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
     k_write_records<<<grid_for(n), TPB, 0, st>>>(E, n, D->cand_off.p, D->rr.p, D->rep.p, D->text_off.p, D->text.p, D->junc_off.p, D->junc.p);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[13], st));
+    compute_turn_end(c);                     // the next batch's kernels (any context of this device) may start: the copies below run under them
     c->stats.kernel_launches += 14;
 
     // ---- only the final records cross PCIe.  Their sizes are known on the device only: the copies cover what the previous

@@ -92,6 +92,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     __shared__ int s_next;
     if (threadIdx.x == 0) { s_L2[0] = ix.L2[0]; s_L2[1] = ix.L2[1]; s_L2[2] = ix.L2[2]; s_L2[3] = ix.L2[3]; s_L2[4] = ix.L2[4]; }
     if (threadIdx.x == 0) s_next = blockIdx.x * per_cta;
+    if (threadIdx.x == 0 && blockIdx.x == 0) a.nhits[a.n_reads] = 0;     // terminator of the prefix sum over the hit counts
     __syncthreads();
     const int r_end = (blockIdx.x + 1) * per_cta;            // own range; [steal_base, n_reads) is shared by everyone
     const IdxT primary = (IdxT)ix.primary;
@@ -268,7 +269,6 @@ void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
     a.turn_batch = turn_batch;
     static const int end_batch = getenv("DARTGPU_END_BATCH") ? atoi(getenv("DARTGPU_END_BATCH")) : 4;
     a.end_batch = end_batch;
-    cudaMemsetAsync(a.steal, 0, sizeof(uint32_t), st);
     if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
     else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
 }
@@ -280,9 +280,16 @@ struct U32ToI64 { __host__ __device__ int64_t operator()(const uint32_t &v) cons
 
 size_t scan_tmp_bytes(int n)
 {
+    // the size query walks the dispatch layer of cub (device attributes, kernel attributes): ~10 us of host time, paid for
+    // every prefix sum of every batch on the one host thread that drives a GPU -- remember the answers
+    static thread_local int last_n[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    static thread_local size_t last_bytes[8];
+    static thread_local int next = 0;
+    for (int i = 0; i < 8; i++) if (last_n[i] == n) return last_bytes[i];
     size_t bytes = 0;
     cub::TransformInputIterator<int64_t, U32ToI64, const uint32_t *> it((const uint32_t *)nullptr, U32ToI64());
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (int64_t *)nullptr, n + 1);
+    last_n[next] = n; last_bytes[next] = bytes; next = (next + 1) & 7;
     return bytes;
 }
 
@@ -570,8 +577,6 @@ void launch_sort_cluster(const DevIndex &ix, const SeedLaunch &a, cudaStream_t s
 {
     if (a.n_reads <= 0) return;
     const int sms = sm_count();
-    cudaMemsetAsync(a.big_count, 0, sizeof(uint32_t), st);
-    cudaMemsetAsync(a.mid_count, 0, sizeof(uint32_t), st);
     int64_t want = ((int64_t)a.n_reads * 8 + 255) / 256;
     int grid = (int)(want < sms * 8 ? want : sms * 8);
     k_sort_cluster_small<<<grid, 256, 0, st>>>(ix, a);

@@ -218,6 +218,7 @@ typedef struct {
     uint64_t kmer_jobs, kmer_window_bases, kmer_read_bases;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t search_sector_loads;     /* 32-byte Occ / start-table sectors the search kernel really requested */
+    double   ms_submit;               /* host time of dartgpu_submit (staging + enqueueing the batch), part of ms_host */
 } dartgpu_stats;
 
 int dartgpu_get_stats(const dartgpu_ctx *ctx, dartgpu_stats *out);
