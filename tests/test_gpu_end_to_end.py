@@ -136,3 +136,40 @@ def test_pool_overflow_is_retried_not_truncated(monkeypatch):
     monkeypatch.setenv("DARTGPU_CAP_SHRINK", "1000")
     gs, gj = _run_gpu(w, (), tag="gpu_shrunk")
     _compare(gs, rs, gj, rj)
+
+
+def _run_patched(w, extra=(), tag="dart_gpu", threads=1, env_extra=None):
+    """oracle/_ref/dart_gpu = the reference's own binary (its CLI, reader, SAM writer) with integration/dart_gpu.patch applied:
+    ReadMapping()'s per-read loop runs in libdartgpu.so."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dart_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dart_gpu is not built")
+    sam, junc = os.path.join(w["dir"], f"{tag}.sam"), os.path.join(w["dir"], f"{tag}.junc")
+    cmd = [exe, "-i", w["idx"], "-f", w["r1"]] + (["-f2", w["r2"]] if w["r2"] else [])
+    cmd += ["-t", str(threads), "-o", sam, "-j", junc] + list(w["flags"]) + list(extra)
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, env=env)
+    return sam, junc
+
+
+@pytest.mark.parametrize("name,extra", [("c1", ()), ("c2", ()), ("c3", ("-mis", "5")), ("c5", ())])
+def test_patched_reference_binary_is_byte_identical(name, extra):
+    """The boundary as an artefact: integration/dart_gpu.patch + dart_gpu_glue.cpp built into the reference
+    (/root/reference/src/Mapping.cpp:598-640, main.cpp:220-223).  Output of `dart_gpu -t 1` == `dart_canon -t 1`, byte for byte,
+    with batches of 8000 reads so that several GPU calls and chunk boundaries are exercised."""
+    w = workload(name)
+    tag = "mis5" if extra else "named"
+    rs, rj = run_reference(w, "dart_canon", 1, extra, tag="ref_" + tag)
+    gs, gj = _run_patched(w, extra, tag="patched_" + tag, env_extra={"DART_GPU_BATCH": "8000"})
+    _compare(gs, rs, gj, rj)
+
+
+def test_patched_reference_binary_with_worker_threads():
+    """-t 3: three reference worker threads, three GPU contexts sharing one resident index; chunks are written in completion
+    order, so the records are compared as a multiset."""
+    w = workload("c3")
+    rs, rj = run_reference(w, "dart_canon", 1, ("-mis", "5"), tag="ref_mis5")
+    gs, gj = _run_patched(w, ("-mis", "5"), tag="patched_t3", threads=3, env_extra={"DART_GPU_BATCH": "8000", "DART_GPU_DEVICES": "0,0"})
+    assert sorted(_records(gs)) == sorted(_records(rs))
+    assert open(gj).read() == open(rj).read()
