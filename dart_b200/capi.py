@@ -51,6 +51,16 @@ class _MapResult(C.Structure):
                 ("cigars", C.c_void_p), ("n_cigar_bytes", C.c_int64), ("junctions", C.c_void_p), ("n_junctions", C.c_int64)]
 
 
+class _FastqBlock(C.Structure):
+    _fields_ = [("text1", C.c_void_p), ("len1", C.c_int64), ("text2", C.c_void_p), ("len2", C.c_int64), ("n_records", C.c_int32),
+                ("fastq", C.c_int32), ("max_read_len", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _SamResult(C.Structure):
+    _fields_ = [("sam", C.c_void_p), ("n_bytes", C.c_int64), ("n_reads", C.c_int64), ("n_unmapped", C.c_int64), ("n_unique", C.c_int64),
+                ("n_paired", C.c_int64), ("junctions", C.c_void_p), ("n_junctions", C.c_int64)]
+
+
 class Stats(C.Structure):
     _fields_ = ([(n, C.c_double) for n in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_h2d",
                                            "ms_d2h", "ms_total_device", "ms_host", "ms_report")] +
@@ -79,7 +89,8 @@ EXPORTS = ["dartgpu_default_params", "dartgpu_create", "dartgpu_create_from_file
            "dartgpu_kmer_reseed", "dartgpu_nw_align", "dartgpu_map_reads", "dartgpu_get_stats",
            "dartgpu_upload_reads", "dartgpu_seed_and_cluster_resident", "dartgpu_synchronize",
            "dartgpu_map_reads_resident", "dartgpu_index_build", "dartgpu_measure_int32_peak", "dartgpu_measure_l2_peak",
-           "dartgpu_submit", "dartgpu_submit_resident", "dartgpu_wait"]
+           "dartgpu_submit", "dartgpu_submit_resident", "dartgpu_wait", "dartgpu_submit_fastq", "dartgpu_wait_sam",
+           "dartgpu_fastq_cut", "dartgpu_alloc_pinned", "dartgpu_free_pinned"]
 
 
 def load_library() -> C.CDLL:
@@ -110,6 +121,10 @@ def load_library() -> C.CDLL:
     L.dartgpu_submit.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.dartgpu_submit_resident.argtypes = [C.c_void_p]
     L.dartgpu_wait.argtypes = [C.c_void_p, C.POINTER(_MapResult)]
+    L.dartgpu_submit_fastq.argtypes = [C.c_void_p, C.POINTER(_FastqBlock)]
+    L.dartgpu_wait_sam.argtypes = [C.c_void_p, C.POINTER(_SamResult)]
+    L.dartgpu_fastq_cut.restype = C.c_int64
+    L.dartgpu_fastq_cut.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32)]
     L.dartgpu_measure_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.dartgpu_measure_l2_peak.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]
     L.dartgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -283,6 +298,27 @@ class Mapper:
         out = _MapResult()
         self._check(self.L.dartgpu_wait(self.h, C.byref(out)))
         return self._result(out, copy)
+
+    # ---- FASTQ text in, SAM text out (device-side ingest and formatting) ----
+    def submit_fastq(self, text1, text2=None, n_records=None, max_read_len=0):
+        """text1 / text2: bytes-like or uint8 arrays (page-locked arrays are DMA'd as they are). Returns at once."""
+        a1 = np.frombuffer(text1, dtype=np.uint8) if not isinstance(text1, np.ndarray) else text1
+        a2 = None if text2 is None else (np.frombuffer(text2, dtype=np.uint8) if not isinstance(text2, np.ndarray) else text2)
+        if n_records is None:
+            k = C.c_int32(0)
+            used = self.L.dartgpu_fastq_cut(a1.ctypes.data, len(a1), 0, C.byref(k))
+            assert used == len(a1), "text1 does not end at a record boundary"
+            n_records = k.value
+        self._held = (a1, a2)
+        b = _FastqBlock(a1.ctypes.data if len(a1) else None, len(a1), a2.ctypes.data if a2 is not None and len(a2) else None,
+                        len(a2) if a2 is not None else 0, n_records, 1, max_read_len, 0)
+        self._check(self.L.dartgpu_submit_fastq(self.h, C.byref(b)))
+
+    def wait_sam(self) -> dict:
+        out = _SamResult()
+        self._check(self.L.dartgpu_wait_sam(self.h, C.byref(out)))
+        return dict(sam=_view(out.sam, np.uint8, out.n_bytes).tobytes(), n_reads=out.n_reads, n_unmapped=out.n_unmapped,
+                    n_unique=out.n_unique, n_paired=out.n_paired, junctions=_view(out.junctions, JUNCTION, out.n_junctions).copy())
 
     def map_reads(self, reads: ReadBatch, resident: bool = False, copy: bool = True) -> dict:
         out = _MapResult()

@@ -68,7 +68,7 @@ void stats_begin(dartgpu_ctx *c)
 // a fresh control block for the batch (or for its next attempt)
 static void ctl_begin(dartgpu_ctx *c)
 {
-    launch_zero(c->d_ctl.p, sizeof(BatchCtl), c->stream);
+    launch_zero(c->d_ctl.p, BATCHCTL_RESET_BYTES, c->stream);      // the ingest fields behind it belong to the upload, not to the attempt
 }
 static void ctl_fetch(dartgpu_ctx *c)      // enqueue the read-back of the control block (a one-warp kernel, not the copy engine)
 {
@@ -97,6 +97,7 @@ static void caps_for_batch(dartgpu_ctx *c)
     atleast(K.nw_ops[1], n * L / 8 + 65536);
     atleast(K.nw_flags, n * L / 8 + 65536);
     atleast(K.nw_aux, n * L / 32 + 65536);
+    if (c->emit_sam) atleast(K.sam, n * (2 * L + 128));
 }
 
 // Grows whatever the aborted attempt is known to need (+25 %).  An attempt stops at the first pool that overflows, so the
@@ -120,6 +121,12 @@ static void caps_grow(dartgpu_ctx *c, const BatchCtl &H)
     const bool cig = need(K.cig, H.cig_total);
     const bool text = need(K.text, H.text_total);
     const bool junc = need(K.junc, H.junc_total);
+    need(K.sam, H.sam_bytes);
+    if (H.abort & CAP_RLEN) {          // a read longer than the bound the scratch was sized for (FASTQ ingest): take the real maximum
+        c->fq.rlen_seen = std::max(c->fq.rlen_seen, (int)H.ingest_max_rlen);
+        c->max_rlen = c->fq.rlen_seen;
+        c->cap_rec = std::max(1, (c->max_rlen + 15) / 16);
+    }
     f = std::min(f, 64.0);
     auto scale = [&](int64_t &cap) { cap = (int64_t)((double)cap * f * 1.1) + 4096; };
     // everything downstream of the first overflow has not been counted yet
@@ -136,6 +143,8 @@ static void check_ctl_errors(const BatchCtl &H)
     if (H.err & ERR_CIGAR_POOL) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("CIGAR pool capacity exceeded"));
     if (H.err & ERR_SORT_SCRATCH) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("seed sort scratch overflow"));
     if (H.err & ERR_NW_WIDTH) throw std::make_pair(DARTGPU_ERR_CUDA, std::string("NW job wider than the row buffer"));
+    if (H.ingest_err & ERR_FASTQ_LINES) throw std::make_pair(DARTGPU_ERR_ARG, std::string("FASTQ block: line count does not match 4 x n_records"));
+    if (H.ingest_err & ERR_READ_TOO_LONG) throw std::make_pair(DARTGPU_ERR_READ_TOO_LONG, std::string("a read is longer than DARTGPU_MAX_RLEN"));
 }
 
 void add_ms(dartgpu_ctx *c, double *slot, cudaEvent_t a, cudaEvent_t b)
@@ -152,6 +161,8 @@ void upload_reads(dartgpu_ctx *c, const dartgpu_reads *reads)
 {
     const int n = reads->n_reads;
     if (n < 0 || (n > 0 && (!reads->bases || !reads->offsets))) throw std::make_pair(DARTGPU_ERR_ARG, std::string("bad read batch"));
+    c->from_fastq = false;
+    launch_zero(&c->d_ctl.p->ingest_err, sizeof(BatchCtl) - BATCHCTL_RESET_BYTES, c->stream);
     const int threads = c->prm.host_threads > 0 ? c->prm.host_threads : omp_get_max_threads();
     int max_rlen = 0, bad = 0;
 #pragma omp parallel for schedule(static) num_threads(threads) reduction(max : max_rlen) reduction(| : bad)
@@ -916,23 +927,33 @@ int dartgpu_nw_align(dartgpu_ctx *c, const char *bases, int64_t n_bases, const d
 // ---- the whole per-read path: submit (enqueue everything, return) / wait (sleep until the batch is done) ----
 namespace dartgpu {
 // everything of one attempt behind the (already enqueued or resident) read upload; records the `done` event
+__global__ void k_ctl_ingest(BatchCtl *ctl, int max_rlen_host)
+{
+    if (ctl->ingest_err) atomicOr(&ctl->abort, 1 << 30);   // bad text: nothing downstream may run
+    else if (ctl->ingest_max_rlen > max_rlen_host) atomicOr(&ctl->abort, CAP_RLEN);
+}
+
 static void enqueue_whole_path(dartgpu_ctx *c)
 {
     compute_turn_begin(c);
     ctl_begin(c);
+    if (c->from_fastq) k_ctl_ingest<<<1, 1, 0, c->stream>>>(c->d_ctl.p, c->max_rlen);
     enqueue_seeding(c);
     enqueue_pipeline(c);
     ctl_fetch(c);
     DG_CUDA(cudaEventRecord(c->done, c->stream));
 }
 
-static void submit_batch(dartgpu_ctx *c, const dartgpu_reads *reads)
-{   // reads == nullptr: the batch uploaded with dartgpu_upload_reads
+static void submit_batch(dartgpu_ctx *c, const dartgpu_reads *reads, const dartgpu_fastq_block *fq = nullptr)
+{   // reads == nullptr and fq == nullptr: the batch uploaded with dartgpu_upload_reads
     Timer t;
     uint64_t rb = c->stats.read_bases;
     stats_begin(c);
-    if (reads) upload_reads(c, reads); else c->stats.read_bases = rb;
-    c->timed_upload = reads != nullptr;
+    c->emit_sam = fq != nullptr;
+    if (fq) upload_fastq(c, fq);
+    else if (reads) upload_reads(c, reads);
+    else c->stats.read_bases = rb;
+    c->timed_upload = reads != nullptr || fq != nullptr;
     c->whole_path = true;
     c->attempts = 0;
     if (c->n_reads > 0) {
@@ -943,14 +964,19 @@ static void submit_batch(dartgpu_ctx *c, const dartgpu_reads *reads)
     c->t_submit_ms = t.ms();
 }
 
-static void wait_batch(dartgpu_ctx *c, dartgpu_map_result *out)
+static void wait_batch(dartgpu_ctx *c, dartgpu_map_result *out, dartgpu_sam_result *sam_out)
 {
     Timer t;
     c->in_flight = false;
-    if (c->n_reads == 0) { *out = dartgpu_map_result{nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0}; return; }
+    if (c->n_reads == 0) {
+        if (out) *out = dartgpu_map_result{nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0};
+        if (sam_out) *sam_out = dartgpu_sam_result{nullptr, 0, 0, 0, 0, 0, nullptr, 0};
+        return;
+    }
     for (;;) {
         DG_CUDA(cudaEventSynchronize(c->done));            // the batch's one wait: a sleeping thread, not a spinning one
         const BatchCtl &H = c->h_ctl.p[0];
+        if (H.ingest_err) check_ctl_errors(H);
         if (!H.abort) break;
         // a pool was too small (first batch of a context, or a batch unlike the ones before): grow it and run the batch again
         if (++c->attempts > 12) throw std::make_pair(DARTGPU_ERR_NOMEM, std::string("device pools keep overflowing"));
@@ -960,7 +986,8 @@ static void wait_batch(dartgpu_ctx *c, dartgpu_map_result *out)
         c->stats.kernel_launches = keep_launches;        // only the attempt that goes through is counted
     }
     check_ctl_errors(c->h_ctl.p[0]);
-    finish_pipeline(c, out);
+    if (sam_out) finish_sam(c, sam_out); else finish_pipeline(c, out);
+    if (c->from_fastq) c->stats.read_bases = c->h_ctl.p[0].ingest_bases;
     collect_stats(c, true);
     c->stats.ms_host = c->t_submit_ms + t.ms();
     c->stats.ms_submit = c->t_submit_ms;
@@ -983,11 +1010,52 @@ int dartgpu_submit_resident(dartgpu_ctx *c)
     return guarded(c, [&] { submit_batch(c, nullptr); });
 }
 
+int dartgpu_submit_fastq(dartgpu_ctx *c, const dartgpu_fastq_block *block)
+{
+    if (!c || !block) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
+    return guarded(c, [&] { submit_batch(c, nullptr, block); });
+}
+
+int dartgpu_wait_sam(dartgpu_ctx *c, dartgpu_sam_result *out)
+{
+    if (!c || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
+    if (!c->in_flight || !c->emit_sam) return fail(c, DARTGPU_ERR_ARG, "no FASTQ batch in flight on this context");
+    int rc = guarded(c, [&] { wait_batch(c, nullptr, out); });
+    if (rc != DARTGPU_OK) { c->in_flight = false; cudaStreamSynchronize(c->stream); cudaGetLastError(); }
+    return rc;
+}
+
+void *dartgpu_alloc_pinned(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void dartgpu_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+// Cuts a buffer of FASTQ text at a record boundary: counts newlines (memchr) up to `max_records` records and returns the
+// bytes they span; *n_records = complete records found.  A last line without '\n' is not counted (read more, or append one).
+int64_t dartgpu_fastq_cut(const char *text, int64_t len, int32_t max_records, int32_t *n_records)
+{
+    int64_t lines = 0, end_of_record = 0;
+    const char *p = text, *e = text + (len > 0 ? len : 0);
+    const int64_t want = 4ll * (max_records > 0 ? max_records : INT32_MAX / 8);
+    while (p < e && lines < want) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+        if (!nl) break;
+        p = nl + 1;
+        if ((++lines & 3) == 0) end_of_record = p - text;
+    }
+    if (n_records) *n_records = (int32_t)(lines / 4);
+    return end_of_record;
+}
+
 int dartgpu_wait(dartgpu_ctx *c, dartgpu_map_result *out)
 {
     if (!c || !out) return fail(c, DARTGPU_ERR_ARG, "NULL argument");
-    if (!c->in_flight) return fail(c, DARTGPU_ERR_ARG, "no batch in flight on this context");
-    int rc = guarded(c, [&] { wait_batch(c, out); });
+    if (!c->in_flight || c->emit_sam) return fail(c, DARTGPU_ERR_ARG, "no batch in flight on this context");
+    int rc = guarded(c, [&] { wait_batch(c, out, nullptr); });
     if (rc != DARTGPU_OK) { c->in_flight = false; cudaStreamSynchronize(c->stream); cudaGetLastError(); }
     return rc;
 }

@@ -27,6 +27,7 @@ struct SharedIndex {
     DevBuf<KmerStart> d_ktab;       // search-start table
     DevBuf<uint32_t> d_ref2;
     DevBuf<int64_t> d_ends;
+    DevBuf<char> d_chr_names; DevBuf<int32_t> d_chr_name_off;   // sequence names for the device-side SAM text
     // Batches of the contexts of this device run their KERNELS in submission order (see compute_turn_begin in capi.cu):
     // the event behind the kernels of the most recently submitted batch, and the context that owns it.
     std::mutex turn_mutex;
@@ -42,8 +43,20 @@ namespace dartgpu {
 // Capacities of the per-batch device pools whose fill is only known on the device (BatchCtl, dartgpu_internal.h).
 // They only ever grow: from the batch's size the first time, from the control block of an aborted batch afterwards.
 struct Caps {
-    int64_t seeds = 0, cands = 0, pool = 0, krecs = 0, cig = 0, text = 0, junc = 0;
+    int64_t seeds = 0, cands = 0, pool = 0, krecs = 0, cig = 0, text = 0, junc = 0, sam = 0;
     int64_t nw_ops[2] = {0, 0}, nw_flags = 0, nw_aux = 0;
+};
+// device side of dartgpu_submit_fastq (sam_kernels.cu): the raw FASTQ text of the batch and where every read's name,
+// bases and qualities sit in it; the SAM text pool
+struct FastqDev {
+    DevBuf<uint8_t> text;
+    DevBuf<int64_t> ls1, ls2, off1, off2, seq_pos, name_pos, qual_pos, unit_off;
+    DevBuf<uint32_t> cnt1, cnt2, unit_bytes;
+    DevBuf<int32_t> name_len, qual_len;
+    DevBuf<char> sam;
+    PinBuf<char> h_sam;
+    int64_t sent_sam = 0, last_sam = -1;
+    int rlen_seen = 0;                      // longest read seen so far on this context (sizes scratch; verified on the device)
 };
 } // namespace dartgpu
 
@@ -84,6 +97,8 @@ struct dartgpu_ctx {
     int64_t total_seeds = 0;
     // ---- the batch in flight (dartgpu_submit .. dartgpu_wait) ----
     bool in_flight = false, whole_path = false, timed_upload = false;
+    bool from_fastq = false, emit_sam = false;    // the batch came as FASTQ text / leaves as SAM text (dartgpu_submit_fastq)
+    dartgpu::FastqDev fq;
     int attempts = 0;
     cudaEvent_t done = nullptr;                   // blocking-sync event recorded behind the batch
     cudaEvent_t compute_done = nullptr;           // recorded behind the batch's last kernel, before its result copies
@@ -144,10 +159,14 @@ void run_kmer(dartgpu_ctx *c, const uint8_t *codes_dev, const KmerJobDev *jobs, 
 void run_nw(dartgpu_ctx *c, const uint8_t *codes_dev, NwJobDev *jobs, int n_jobs);
 // the whole per-read path over the uploaded batch: device orchestration, enqueued behind the seeding kernels
 void enqueue_pipeline(dartgpu_ctx *c);
+// sam_kernels.cu
+void upload_fastq(dartgpu_ctx *c, const dartgpu_fastq_block *b);          // H2D of the raw text + parse + encode on the device
+void enqueue_sam(dartgpu_ctx *c, const dartgpu_read_result *rr, const dartgpu_report *rep, const char *cigars);
 // Kernels of different contexts of one device take turns (FIFO) instead of time-sharing the SMs: see capi.cu
 void compute_turn_begin(dartgpu_ctx *c);
 void compute_turn_end(dartgpu_ctx *c);
 void finish_pipeline(dartgpu_ctx *c, dartgpu_map_result *out);          // after the batch's synchronisation
+void finish_sam(dartgpu_ctx *c, dartgpu_sam_result *out);
 void free_device_pipe(void *p);
 
 struct Timer {

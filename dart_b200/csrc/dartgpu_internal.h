@@ -1,6 +1,7 @@
 // Internal declarations shared by the CUDA kernels, the host orchestration and the C-ABI glue.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -75,8 +76,8 @@ struct DevStats {            // device-side work counters (see dartgpu_stats)
 // looks at this block exactly once per batch, together with the results -- grows the pool and runs the batch again.
 // In steady state (batches of similar size) no batch is ever repeated and the host synchronises once per batch.
 enum { CAP_SEEDS = 1, CAP_CANDS = 2, CAP_POOL = 4, CAP_KRECS = 8, CAP_NW_B = 16, CAP_NW_C = 32, CAP_CIG = 64, CAP_TEXT = 128,
-       CAP_JUNC = 256 };
-enum { ERR_CIGAR_POOL = 1, ERR_SORT_SCRATCH = 2, ERR_NW_WIDTH = 4 };
+       CAP_JUNC = 256, CAP_SAM = 512, CAP_RLEN = 1024 };
+enum { ERR_CIGAR_POOL = 1, ERR_SORT_SCRATCH = 2, ERR_NW_WIDTH = 4, ERR_FASTQ_LINES = 8, ERR_READ_TOO_LONG = 16 };
 struct BatchCtl {
     long long total_seeds, ncand, nrep, pool_total, cig_total, text_total, junc_total, kmer_recs;
     unsigned long long nw_ops[2], nw_flags[2], nw_aux[2];   // pool use of the two NW rounds (B: gap flanks, C: non-simple pairs)
@@ -87,8 +88,15 @@ struct BatchCtl {
     uint32_t steal, big_count, mid_count, heavy_count;    // work-stealing / queue counters of the seeding and 8-mer kernels
     uint32_t pad;
     unsigned long long work[4];                             // [0] NW cells, [1] 8-mer window bases, [2] 8-mer read bases
+    long long sam_bytes;                                    // SAM text of the batch (dartgpu_submit_fastq)
+    unsigned long long sam_counts[4];                       // unmapped reads, unique reads, paired reads (the reference's summary lines)
     DevStats stats;
+    // ---- written by the ingest kernels BEFORE the batch's first attempt and kept across attempts (not part of the reset) ----
+    int32_t ingest_err;                                     // ERR_* bits of the FASTQ parse
+    int32_t ingest_max_rlen;                                // longest read of the batch
+    unsigned long long ingest_bases;
 };
+constexpr size_t BATCHCTL_RESET_BYTES = offsetof(BatchCtl, ingest_err);
 
 // ---------------------------------------------------------------------------------------------------
 // small RAII buffers

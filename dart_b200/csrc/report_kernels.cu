@@ -393,16 +393,32 @@ void enqueue_pipeline(dartgpu_ctx *c)
     D->text.reserve(K.text + 1); D->junc.reserve(K.junc + 1);
     k_write_records<<<grid_for(n), TPB, 0, st>>>(E, n, D->cand_off.p, D->rr.p, D->rep.p, D->text_off.p, D->text.p, D->junc_off.p, D->junc.p);
     DG_CUDA(cudaGetLastError());
-    DG_CUDA(cudaEventRecord(c->ev[13], st));
-    compute_turn_end(c);                     // the next batch's kernels (any context of this device) may start: the copies below run under them
     c->stats.kernel_launches += 14;
-
-    // ---- only the final records cross PCIe.  Their sizes are known on the device only: the copies cover what the previous
-    // batch of this context needed plus a margin (everything the pools can hold the first time); finish_pipeline tops up.
     auto predict = [&](int64_t last, int64_t cap, int64_t first_guess) {
         int64_t want = last < 0 ? first_guess : (int64_t)((double)last * (double)n / std::max(1, D->last_n) * 1.02) + 4096;
         return std::max<int64_t>(0, std::min(want, cap));
     };
+    if (c->emit_sam) {
+        // ---- complete SAM lines on the device (sam_kernels.cu): only text and junction records cross PCIe ----
+        enqueue_sam(c, D->rr.p, D->rep.p, D->text.p);
+        DG_CUDA(cudaEventRecord(c->ev[13], st));
+        compute_turn_end(c);
+        FastqDev &F = c->fq;
+        const int64_t guess = F.last_sam < 0 ? std::min<int64_t>(K.sam, (int64_t)n * (2 * std::max(c->max_rlen, 32) + 96)) : 0;
+        F.sent_sam = predict(F.last_sam, K.sam, guess);
+        D->sent_junc = predict(D->last_junc, K.junc, n / 8 + 4096);
+        D->sent_rep = D->sent_text = 0;
+        F.h_sam.reserve(F.sent_sam + 1); D->h_junc.reserve(D->sent_junc + 1);
+        if (F.sent_sam) DG_CUDA(cudaMemcpyAsync(F.h_sam.p, F.sam.p, (size_t)F.sent_sam, cudaMemcpyDeviceToHost, st));
+        if (D->sent_junc) DG_CUDA(cudaMemcpyAsync(D->h_junc.p, D->junc.p, (size_t)D->sent_junc * sizeof(dartgpu_junction), cudaMemcpyDeviceToHost, st));
+        DG_CUDA(cudaEventRecord(c->ev[14], st));
+        return;
+    }
+    DG_CUDA(cudaEventRecord(c->ev[13], st));
+    compute_turn_end(c);                     // the next batch's kernels (any context of this device) may start: the copies below run under them
+
+    // ---- only the final records cross PCIe.  Their sizes are known on the device only: the copies cover what the previous
+    // batch of this context needed plus a margin (a guess the first time); finish_pipeline tops up.
     D->sent_rep = predict(D->last_rep, cap_r, (int64_t)n + n / 2 + 1024);
     D->sent_text = predict(D->last_text, K.text, 6ll * n + 4096);
     D->sent_junc = predict(D->last_junc, K.junc, n / 8 + 4096);
@@ -443,6 +459,35 @@ void finish_pipeline(dartgpu_ctx *c, dartgpu_map_result *out)
     out->reads = D->h_rr.p; out->n_reads = n;
     out->reports = D->h_rep.p; out->n_reports = nrep;
     out->cigars = D->h_text.p; out->n_cigar_bytes = text_total;
+    out->junctions = D->h_junc.p; out->n_junctions = junc_total;
+}
+
+// dartgpu_wait_sam: the same for a batch whose results are SAM text
+void finish_sam(dartgpu_ctx *c, dartgpu_sam_result *out)
+{
+    DevicePipe *D = pipe_of(c);
+    FastqDev &F = c->fq;
+    cudaStream_t st = c->stream;
+    const BatchCtl &H = c->h_ctl.p[0];
+    const int64_t sam_total = H.sam_bytes, junc_total = H.junc_total;
+    bool more = false;
+    if (sam_total > F.sent_sam) {
+        int64_t sent = F.sent_sam;
+        if ((size_t)sam_total + 1 > F.h_sam.cap) { F.h_sam.reserve(sam_total + 1); sent = 0; }
+        DG_CUDA(cudaMemcpyAsync(F.h_sam.p + sent, F.sam.p + sent, (size_t)(sam_total - sent), cudaMemcpyDeviceToHost, st));
+        more = true;
+    }
+    if (junc_total > D->sent_junc) {
+        int64_t sent = D->sent_junc;
+        if ((size_t)junc_total + 1 > D->h_junc.cap) { D->h_junc.reserve(junc_total + 1); sent = 0; }
+        DG_CUDA(cudaMemcpyAsync(D->h_junc.p + sent, D->junc.p + sent, (size_t)(junc_total - sent) * sizeof(dartgpu_junction), cudaMemcpyDeviceToHost, st));
+        more = true;
+    }
+    if (more) DG_CUDA(dg_stream_sync(st));
+    F.last_sam = sam_total; D->last_junc = junc_total; D->last_n = c->n_reads;
+    c->stats.d2h_bytes += (uint64_t)std::max(sam_total, F.sent_sam) + (uint64_t)std::max(junc_total, D->sent_junc) * sizeof(dartgpu_junction);
+    out->sam = F.h_sam.p; out->n_bytes = sam_total;
+    out->n_reads = c->n_reads; out->n_unmapped = (int64_t)H.sam_counts[0]; out->n_unique = (int64_t)H.sam_counts[1]; out->n_paired = (int64_t)H.sam_counts[2];
     out->junctions = D->h_junc.p; out->n_junctions = junc_total;
 }
 

@@ -223,14 +223,41 @@ static void format_batch(const std::vector<std::string> &seq_names, const Reads 
 }
 
 
+static void write_header(FILE *fo, const std::vector<std::string> &names, const std::vector<int64_t> &lens)
+{
+    fprintf(fo, "@PG\tID:Dart\tPN:Dart\tVN:1.4.6\n");   // Mapping.cpp:741 (VersionStr, main.cpp:13)
+    for (size_t i = 0; i < names.size(); i++) fprintf(fo, "@SQ\tSN:%s\tLN:%lld\n", names[i].c_str(), (long long)lens[i]);
+}
+
+// OutputSpliceJunctions + AbsLoc2ChrLoc (Mapping.cpp:683-716); sj: key -> (type, count)
+static int write_junctions(const char *sj_fn, const std::vector<std::string> &names, const std::vector<int64_t> &lens, int64_t G,
+                           const std::map<std::pair<int64_t, int64_t>, std::pair<int, int>> &sj)
+{
+    FILE *fj = fopen(sj_fn, "w");
+    int nj = 0;
+    if (!fj) return 0;
+    std::vector<int64_t> fwd(names.size() + 1, 0);
+    for (size_t i = 0; i < names.size(); i++) fwd[i + 1] = fwd[i] + lens[i];
+    for (auto &kv : sj) {
+        int64_t g1 = kv.first.first, g2 = kv.first.second;
+        int chr = -1;   // ChrLocMap.lower_bound(g1): forward ends, then reverse-strand ends
+        if (g1 < G) { for (int i = 0; i < (int)fwd.size() - 1; i++) if (g1 <= fwd[i + 1] - 1) { chr = i; break; } }
+        else if (g1 < 2 * G) { for (int i = (int)fwd.size() - 2; i >= 0; i--) if (g1 <= 2 * G - fwd[i] - 1) { chr = i; break; } }
+        if (chr == -1) continue;
+        nj++;
+        fprintf(fj, "%s\t%lld\t%lld\t%d\n", names[chr].c_str(), (long long)(g1 + 1 - fwd[chr]), (long long)(g2 + 1 - fwd[chr]), kv.second.second);
+    }
+    fclose(fj);
+    return nj;
+}
+
 // header + records + junction table, exactly as Mapping() / OutputSpliceJunctions() write them
 static int write_outputs(const char *out_fn, const char *sj_fn, const std::vector<std::string> &names, const std::vector<int64_t> &lens,
                          int64_t G, const std::vector<Out> &outs, int64_t *unm, int64_t *uq, int64_t *prd)
 {
     FILE *fo = fopen(out_fn, "w");
     if (!fo) { fprintf(stderr, "cannot write %s\n", out_fn); return -1; }
-    fprintf(fo, "@PG\tID:Dart\tPN:Dart\tVN:1.4.6\n");   // Mapping.cpp:741 (VersionStr, main.cpp:13)
-    for (size_t i = 0; i < names.size(); i++) fprintf(fo, "@SQ\tSN:%s\tLN:%lld\n", names[i].c_str(), (long long)lens[i]);
+    write_header(fo, names, lens);
     std::map<std::pair<int64_t, int64_t>, std::pair<int, int>> sj; // key -> (type, count); first insert fixes the type
     for (auto &o : outs) {
         fwrite(o.sam.data(), 1, o.sam.size(), fo);
@@ -241,22 +268,5 @@ static int write_outputs(const char *out_fn, const char *sj_fn, const std::vecto
         }
     }
     fclose(fo);
-    // OutputSpliceJunctions + AbsLoc2ChrLoc (Mapping.cpp:683-716)
-    FILE *fj = fopen(sj_fn, "w");
-    int nj = 0;
-    if (fj) {
-        std::vector<int64_t> fwd(names.size() + 1, 0);
-        for (size_t i = 0; i < names.size(); i++) fwd[i + 1] = fwd[i] + lens[i];
-        for (auto &kv : sj) {
-            int64_t g1 = kv.first.first, g2 = kv.first.second;
-            int chr = -1;   // ChrLocMap.lower_bound(g1): forward ends, then reverse-strand ends
-            if (g1 < G) { for (int i = 0; i < (int)fwd.size() - 1; i++) if (g1 <= fwd[i + 1] - 1) { chr = i; break; } }
-            else if (g1 < 2 * G) { for (int i = (int)fwd.size() - 2; i >= 0; i--) if (g1 <= 2 * G - fwd[i] - 1) { chr = i; break; } }
-            if (chr == -1) continue;
-            nj++;
-            fprintf(fj, "%s\t%lld\t%lld\t%d\n", names[chr].c_str(), (long long)(g1 + 1 - fwd[chr]), (long long)(g2 + 1 - fwd[chr]), kv.second.second);
-        }
-        fclose(fj);
-    }
-    return nj;
+    return write_junctions(sj_fn, names, lens, G, sj);
 }

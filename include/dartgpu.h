@@ -203,6 +203,38 @@ int dartgpu_map_reads(dartgpu_ctx *ctx, const dartgpu_reads *reads, dartgpu_map_
 int dartgpu_submit(dartgpu_ctx *ctx, const dartgpu_reads *reads);
 int dartgpu_wait(dartgpu_ctx *ctx, dartgpu_map_result *out);
 
+/* ---- read ingest and SAM text on the device ----------------------------------------------
+ * Replaces, for FASTQ input, GetNextChunk (src/GetData.cpp:134-179: record parsing, header cut, nst_nt4_table encoding,
+ * mate-2 reverse complement + quality reversal) and OutputPairedAlignments / OutputSingledAlignments
+ * (src/Mapping.cpp:208-369: the SAM text of every record): the caller hands over raw blocks of the FASTQ file(s) and gets
+ * back complete SAM lines in input order plus the junction records — the host only reads and writes files.
+ * text1 must start at a record and end with the '\n' that ends a record (dartgpu_fastq_cut finds that point); with two
+ * files (-f / -f2) text2 holds the same number of records and read 2i is record i of text1, read 2i+1 record i of text2;
+ * with one file and params.pair_end (-p) mates alternate in text1.  Page-locked buffers are DMA'd as they are. */
+typedef struct {
+    const char *text1; int64_t len1;
+    const char *text2; int64_t len2;    /* NULL / 0: one file */
+    int32_t     n_records;              /* records in text1 (and in text2) */
+    int32_t     fastq;                  /* FastQFormat; FASTA input is not handled on this path (DARTGPU_ERR_ARG) */
+    int32_t     max_read_len;           /* hint: longest read (0 = take the first record's); a longer read costs one retry */
+    int32_t     reserved;
+} dartgpu_fastq_block;
+
+typedef struct {
+    const char *sam; int64_t n_bytes;   /* SAM lines of the batch, input order, each ending in '\n' */
+    int64_t n_reads, n_unmapped, n_unique, n_paired;   /* the counters behind the reference's summary (Mapping.cpp:803-813) */
+    const dartgpu_junction *junctions; int64_t n_junctions;
+} dartgpu_sam_result;
+
+int dartgpu_submit_fastq(dartgpu_ctx *ctx, const dartgpu_fastq_block *block);
+int dartgpu_wait_sam(dartgpu_ctx *ctx, dartgpu_sam_result *out);
+/* Page-locked host memory for the blocks (so that a caller that links nothing but this library can have its file reads
+ * DMA'd without a staging copy). */
+void *dartgpu_alloc_pinned(uint64_t bytes);
+void  dartgpu_free_pinned(void *p);
+/* Host helper: how many bytes of `text` hold at most max_records complete 4-line records (0 = no limit)? */
+int64_t dartgpu_fastq_cut(const char *text, int64_t len, int32_t max_records, int32_t *n_records);
+
 /* ---- measurement ------------------------------------------------------------------------------------------
  * Device time (CUDA events on the context's stream) and algorithmic work of the kernels launched by the LAST
  * call, for roofline reporting. */

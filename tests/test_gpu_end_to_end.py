@@ -173,3 +173,63 @@ def test_patched_reference_binary_with_worker_threads():
     gs, gj = _run_patched(w, ("-mis", "5"), tag="patched_t3", threads=3, env_extra={"DART_GPU_BATCH": "8000", "DART_GPU_DEVICES": "0,0"})
     assert sorted(_records(gs)) == sorted(_records(rs))
     assert open(gj).read() == open(rj).read()
+
+
+def test_host_reader_path_still_matches():
+    """-hostpath: the stand-in host reader / formatter over dartgpu_map_reads (the path FASTA input takes)."""
+    w = workload("c3")
+    rs, rj = run_reference(w, "dart_canon", 1, ("-mis", "5"), tag="ref_mis5")
+    gs, gj = _run_gpu(w, ("-mis", "5"), tag="gpu_hostpath", more=("-hostpath", "-batch", "700"))
+    _compare(gs, rs, gj, rj)
+
+
+def test_device_ingest_and_sam_text_on_awkward_fastq(tmp_path):
+    """GPU-side FASTQ parsing and SAM text against the reference's reader / writer (GetData.cpp:77-179, Mapping.cpp:208-369) on
+    records that exercise their corners: lower-case and ambiguous bases in both mates (mate 2 is reverse-complemented with
+    GetComplementaryBase: anything but ACGT/acgt becomes N; a forward-strand mate-2 record prints the complement of THAT),
+    reads of different lengths, headers with '/', blanks, tabs and leading '@@', a last line without its newline."""
+    import random
+    need = os.path.join(ROOT, "oracle", "_ref", "dart_canon")
+    if not os.path.exists(need):
+        pytest.skip("oracle/_ref is not built")
+    rng = random.Random(7)
+
+    def recs(path):
+        L = open(path).read().split("\n")
+        return [L[i:i + 4] for i in range(0, len(L) - 3, 4)]
+    r1, r2 = recs(os.path.join(GOLDEN, "pe1.fq")), recs(os.path.join(GOLDEN, "pe2.fq"))
+    for k, (a, b) in enumerate(zip(r1, r2)):
+        for r in (a, b):
+            s = list(r[1])
+            mode = (k + (r is b)) % 6
+            if mode == 0:
+                for _ in range(3):
+                    p = rng.randrange(len(s)); s[p] = s[p].lower()
+            elif mode == 1:
+                s[rng.randrange(len(s))] = "N"
+            elif mode == 2:
+                s[rng.randrange(len(s))] = rng.choice("RYKMn")
+            elif mode == 3:
+                cut = rng.randrange(40, len(s)); s = s[:cut]; r[3] = r[3][:cut]
+            r[1] = "".join(s)
+        base = a[0].split("/")[0].split(" ")[0]
+        style = k % 5
+        if style == 1:
+            a[0], b[0] = base + " first mate", base + " second mate"
+        elif style == 2:
+            a[0], b[0] = base + "\tx", base + "\ty"
+        elif style == 3:
+            a[0], b[0] = "@" + base + "/1", "@" + base + "/2"
+    d = str(tmp_path)
+    for name, rr in (("a1.fq", r1), ("a2.fq", r2)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write("\n".join("\n".join(r) for r in rr))        # no newline behind the last quality line
+    w = dict(dir=d, idx=GOLDEN + "/idx", r1=os.path.join(d, "a1.fq"), r2=os.path.join(d, "a2.fq"), flags=["-mis", "5"])
+    for extra, tag in (((), "plain"), (("-m",), "multi")):
+        rs, rj = run_reference(w, "dart_canon", 1, extra, tag="ref_" + tag)
+        gs, gj = _run_gpu(w, extra, tag="gpu_" + tag, more=("-batch", "64"))
+        _compare(gs, rs, gj, rj)
+    w1 = dict(w, r2=None)
+    rs, rj = run_reference(w1, "dart_canon", 1, (), tag="ref_se")
+    gs, gj = _run_gpu(w1, (), tag="gpu_se", more=("-batch", "50"))
+    _compare(gs, rs, gj, rj)
