@@ -575,6 +575,14 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
     }
     std::sort(ends.begin(), ends.end());
     for (auto &p : ends) { S->ends.push_back(p.first); S->end_chr.push_back(p.second); }
+    {   // sequence names for the device-side SAM text (sam_kernels.cu)
+        std::string all; std::vector<int32_t> off{0};
+        for (auto &nm : S->names) { all += nm; off.push_back((int32_t)all.size()); }
+        S->d_chr_names.reserve(all.size() + 1); S->d_chr_name_off.reserve(off.size());
+        DG_CUDA(cudaMemcpyAsync(S->d_chr_names.p, all.data(), all.size(), cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemcpyAsync(S->d_chr_name_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+        DG_CUDA(dg_stream_sync(st));
+    }
 
     DevIndex &ix = S->ix;
     ix.n_blocks32 = n_blocks32;
@@ -691,6 +699,7 @@ static void build_context(dartgpu_ctx *c, const dartgpu_index_view *v)
     c->ix = c->shared->ix;
     c->G = c->shared->G;
     c->d_ctl.reserve(1); c->h_ctl.reserve(1);
+    launch_zero(c->d_ctl.p, sizeof(BatchCtl), c->stream);     // incl. the ingest fields, which only the uploads reset
     DG_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventBlockingSync | cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming));
     DG_CUDA(dg_stream_sync(c->stream));

@@ -473,16 +473,6 @@ void enqueue_sam(dartgpu_ctx *c, const dartgpu_read_result *rr, const dartgpu_re
     cudaStream_t st = c->stream;
     const int n = c->n_reads, paired = c->prm.pair_end != 0, units = paired ? n / 2 : n;
     SharedIndex &X = *c->shared;
-    if (!X.d_chr_names.p) {          // once per device
-        std::lock_guard<std::mutex> lock(X.turn_mutex);
-        if (!X.d_chr_names.p) {
-            std::string all; std::vector<int32_t> off{0};
-            for (auto &s : X.names) { all += s; off.push_back((int32_t)all.size()); }
-            X.d_chr_names.reserve(all.size() + 1); X.d_chr_name_off.reserve(off.size());
-            DG_CUDA(cudaMemcpy(X.d_chr_names.p, all.data(), all.size(), cudaMemcpyHostToDevice));
-            DG_CUDA(cudaMemcpy(X.d_chr_name_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-        }
-    }
     SamDev S{};
     S.n_reads = n; S.paired = paired; S.multi_hit = c->prm.multi_hit; S.unique = c->prm.unique;
     S.rr = rr; S.rep = rep; S.cigars = cigars; S.text = F.text.p;
