@@ -71,8 +71,8 @@ int main(int argc, char **argv)
     dartgpu_params P; dartgpu_default_params(&P);
     const char *index = nullptr, *f1 = nullptr, *f2 = nullptr, *out_fn = "output.sam", *sj_fn = "junctions.tab";
     bool interleaved = false, want_stats = false, hostpath = false;
-    int64_t batch = 1 << 20;
-    int inflight = 3;
+    int64_t batch = 1 << 19;
+    int inflight = 4;
     std::vector<int> devices{0};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -159,38 +159,48 @@ int main(int argc, char **argv)
         n_reads_total = n;
     } else {
         // ---- streaming path: raw FASTQ blocks -> GPU -> SAM text ----
-        FILE *fo = fopen(out_fn, "w");
-        if (!fo) { fprintf(stderr, "cannot write %s\n", out_fn); return 1; }
-        setvbuf(fo, nullptr, _IONBF, 0);
-        write_header(fo, names, lens);
+        const int out_fd = open(out_fn, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (out_fd < 0) { fprintf(stderr, "cannot write %s\n", out_fn); return 1; }
+        int64_t file_off = 0;
+        {
+            std::string h = "@PG\tID:Dart\tPN:Dart\tVN:1.4.6\n";   // Mapping.cpp:741 (VersionStr, main.cpp:13)
+            for (size_t i = 0; i < names.size(); i++) h += "@SQ\tSN:" + names[i] + "\tLN:" + std::to_string(lens[i]) + "\n";
+            if (write(out_fd, h.data(), h.size()) != (ssize_t)h.size()) { fprintf(stderr, "cannot write %s\n", out_fn); return 1; }
+            file_off = (int64_t)h.size();
+        }
         const int rec_per_block = (int)(paired && !f2 ? batch : (f2 ? batch / 2 : batch));   // records of file 1 per block
-        // block buffers: generous for the record count; a block also ends when its buffer is full
         Stream s1, s2;
         s1.fd = open(f1, O_RDONLY);
         if (f2) { s2.fd = open(f2, O_RDONLY); if (s2.fd < 0) { fprintf(stderr, "Cannot access file:[%s]\n", f2); return 1; } }
         int64_t first_rec = 512;
         { char probe[8192]; ssize_t got = pread(s1.fd, probe, sizeof probe, 0); int32_t k = 0; int64_t used = dartgpu_fastq_cut(probe, got > 0 ? got : 0, 1, &k); if (k == 1) first_rec = used; }
-        const int64_t cap = std::max<int64_t>(1 << 20, (int64_t)((double)rec_per_block * (double)first_rec * 1.25) + (1 << 16));
-        const int n_blocks = nd * inflight + 2;
+        // a block buffer holds the wanted records with a little room; a block also ends when its buffer is full
+        const int64_t cap = std::max<int64_t>(1 << 20, (int64_t)((double)rec_per_block * (double)first_rec * 1.06) + (1 << 16));
+        const int n_blocks = nd * inflight + 1;
         std::vector<Block> blocks(n_blocks);
         Pipeline PL; PL.ready.resize(nd);
-        for (auto &b : blocks) {
-            b.cap = cap; b.b1 = (char *)dartgpu_alloc_pinned(cap); b.b2 = f2 ? (char *)dartgpu_alloc_pinned(cap) : nullptr;
-            if (!b.b1 || (f2 && !b.b2)) { fprintf(stderr, "cannot allocate page-locked block buffers\n"); return 1; }
-            PL.free_blocks.push_back(&b);
-        }
+        for (auto &b : blocks) { b.cap = cap; PL.free_blocks.push_back(&b); }   // page-locked on first use, by the reader: pinning
+                                                                                  // 100+ MB takes ~50 ms and now overlaps the GPU
+        // ---- reader: the two files of a block are read and cut by two threads at once ----
         std::thread reader([&] {
             int64_t id = 0;
             for (;;) {
                 Block *b;
                 { std::unique_lock<std::mutex> lk(PL.mu); PL.cv.wait(lk, [&] { return !PL.free_blocks.empty() || PL.failed; }); if (PL.failed) break; b = PL.free_blocks.front(); PL.free_blocks.pop_front(); }
-                const int64_t n1 = s1.fill(b->b1, b->cap - 1);
+                if (!b->b1) {
+                    b->b1 = (char *)dartgpu_alloc_pinned(cap); b->b2 = f2 ? (char *)dartgpu_alloc_pinned(cap) : nullptr;
+                    if (!b->b1 || (f2 && !b->b2)) { fprintf(stderr, "cannot allocate page-locked block buffers\n"); std::lock_guard<std::mutex> lk(PL.mu); PL.failed = true; PL.reader_done = true; PL.cv.notify_all(); return; }
+                }
+                int64_t n1 = 0, n2 = 0, used1 = 0, used2 = 0;
                 int32_t k1 = 0, k2 = 0;
-                int64_t used1 = dartgpu_fastq_cut(b->b1, n1, rec_per_block, &k1), used2 = 0, n2 = 0;
+                std::thread second;
+                if (f2) second = std::thread([&] { n2 = s2.fill(b->b2, b->cap - 1); used2 = dartgpu_fastq_cut(b->b2, n2, rec_per_block, &k2); });
+                n1 = s1.fill(b->b1, b->cap - 1);
+                used1 = dartgpu_fastq_cut(b->b1, n1, rec_per_block, &k1);
                 if (f2) {
-                    n2 = s2.fill(b->b2, b->cap - 1);
-                    used2 = dartgpu_fastq_cut(b->b2, n2, k1, &k2);
-                    if (k2 < k1) used1 = dartgpu_fastq_cut(b->b1, n1, k2, &k1);      // the shorter file decides (GetData.cpp:152-155)
+                    second.join();
+                    if (k2 < k1) used1 = dartgpu_fastq_cut(b->b1, n1, k2, &k1);      // the shorter side decides (GetData.cpp:152-155)
+                    else if (k1 < k2) used2 = dartgpu_fastq_cut(b->b2, n2, k1, &k2);
                     s2.keep(b->b2, used2, n2);
                 } else if (paired && (k1 & 1)) used1 = dartgpu_fastq_cut(b->b1, n1, k1 - 1, &k1);   // -p: mates stay together
                 s1.keep(b->b1, used1, n1);
@@ -203,38 +213,67 @@ int main(int argc, char **argv)
             { std::lock_guard<std::mutex> lk(PL.mu); PL.reader_done = true; }
             PL.cv.notify_all();
         });
+        // ---- writers: a block's text goes to its place in the file (pwrite) while later blocks are already being mapped ----
+        struct WriteJob { const char *p; int64_t n, off; int d; dartgpu_ctx *c; Block *b; };
+        std::deque<WriteJob> wq;
+        std::vector<std::deque<dartgpu_ctx *>> free_ctx(nd);
+        for (int d = 0; d < nd; d++) for (auto c : ctx[d]) free_ctx[d].push_back(c);
+        int writes_pending = 0;
+        bool workers_done = false;
+        auto writer = [&] {
+            for (;;) {
+                WriteJob j;
+                {
+                    std::unique_lock<std::mutex> lk(PL.mu);
+                    PL.cv.wait(lk, [&] { return !wq.empty() || workers_done || PL.failed; });
+                    if (wq.empty()) return;
+                    j = wq.front(); wq.pop_front();
+                }
+                int64_t done = 0;
+                bool ok = true;
+                while (done < j.n) {
+                    ssize_t w = pwrite(out_fd, j.p + done, (size_t)std::min<int64_t>(j.n - done, 1 << 27), j.off + done);
+                    if (w <= 0) { ok = false; break; }
+                    done += w;
+                }
+                {
+                    std::lock_guard<std::mutex> lk(PL.mu);
+                    if (!ok) { fprintf(stderr, "write to %s failed\n", out_fn); PL.failed = true; }
+                    free_ctx[j.d].push_back(j.c); PL.free_blocks.push_back(j.b); writes_pending--;
+                }
+                PL.cv.notify_all();
+            }
+        };
         std::vector<std::map<std::pair<int64_t, int64_t>, std::pair<int, int>>> sj(nd);
         std::vector<int64_t> w_reads(nd, 0), w_unm(nd, 0), w_uq(nd, 0), w_prd(nd, 0);
         auto worker = [&](int d) {
             std::deque<std::pair<dartgpu_ctx *, Block *>> flying;
-            size_t next_ctx = 0;
             auto fail_all = [&](const char *what, dartgpu_ctx *c, int rc) {
                 fprintf(stderr, "%s failed (%d): %s\n", what, rc, dartgpu_last_error(c));
                 { std::lock_guard<std::mutex> lk(PL.mu); PL.failed = true; }
                 PL.cv.notify_all();
             };
             for (;;) {
-                // submit while a context is free and a block is ready (block only when nothing is in flight)
-                while ((int)flying.size() < per_dev) {
-                    Block *b = nullptr;
+                // submit while a context is free and a block is ready; sleep only when nothing is in flight
+                for (;;) {
+                    Block *b = nullptr; dartgpu_ctx *c = nullptr;
                     {
                         std::unique_lock<std::mutex> lk(PL.mu);
-                        if (flying.empty()) PL.cv.wait(lk, [&] { return !PL.ready[d].empty() || PL.reader_done || PL.failed; });
+                        if (flying.empty())
+                            PL.cv.wait(lk, [&] { return (!PL.ready[d].empty() && !free_ctx[d].empty()) || (PL.reader_done && PL.ready[d].empty()) || PL.failed; });
                         if (PL.failed) return;
-                        if (!PL.ready[d].empty()) { b = PL.ready[d].front(); PL.ready[d].pop_front(); }
+                        if (!PL.ready[d].empty() && !free_ctx[d].empty()) {
+                            b = PL.ready[d].front(); PL.ready[d].pop_front();
+                            c = free_ctx[d].front(); free_ctx[d].pop_front();
+                        }
                     }
                     if (!b) break;
-                    dartgpu_ctx *c = ctx[d][next_ctx++ % per_dev];
                     dartgpu_fastq_block fb{b->b1, b->len1, f2 ? b->b2 : nullptr, b->len2, b->n_rec, 1, 0, 0};
                     int rc = dartgpu_submit_fastq(c, &fb);
                     if (rc != DARTGPU_OK) { fail_all("dartgpu_submit_fastq", c, rc); return; }
                     flying.push_back({c, b});
                 }
-                if (flying.empty()) {
-                    std::lock_guard<std::mutex> lk(PL.mu);
-                    if (PL.reader_done && PL.ready[d].empty()) return;
-                    continue;
-                }
+                if (flying.empty()) return;          // reader done, nothing ready, nothing in flight
                 dartgpu_ctx *c = flying.front().first; Block *b = flying.front().second;
                 flying.pop_front();
                 dartgpu_sam_result res;
@@ -247,31 +286,37 @@ int main(int argc, char **argv)
                             (unsigned long long)s.kmer_jobs, s.ms_nw, (unsigned long long)s.nw_jobs, (unsigned long long)s.nw_cells, s.ms_report, s.ms_d2h,
                             s.ms_host, (unsigned long long)s.kernel_launches, res.n_bytes / 1e6);
                 }
-                {   // blocks are written in input order, whichever GPU finishes first
-                    std::unique_lock<std::mutex> lk(PL.mu);
-                    PL.cv.wait(lk, [&] { return PL.next_to_write == b->id || PL.failed; });
-                    if (PL.failed) return;
-                }
-                if (res.n_bytes && fwrite(res.sam, 1, (size_t)res.n_bytes, fo) != (size_t)res.n_bytes) { fail_all("fwrite", c, -1); return; }
                 for (int64_t k = 0; k < res.n_junctions; k++) {
                     const dartgpu_junction &j = res.junctions[k];
                     auto it = sj[d].find({j.g1, j.g2});
                     if (it != sj[d].end()) it->second.second++; else sj[d][{j.g1, j.g2}] = {j.type, 1};
                 }
                 w_reads[d] += res.n_reads; w_unm[d] += res.n_unmapped; w_uq[d] += res.n_unique; w_prd[d] += res.n_paired;
-                { std::lock_guard<std::mutex> lk(PL.mu); PL.next_to_write = b->id + 1; PL.free_blocks.push_back(b); }
+                {   // blocks take their place in the file in input order, whichever GPU finishes first
+                    std::unique_lock<std::mutex> lk(PL.mu);
+                    PL.cv.wait(lk, [&] { return PL.next_to_write == b->id || PL.failed; });
+                    if (PL.failed) return;
+                    wq.push_back(WriteJob{res.sam, res.n_bytes, file_off, d, c, b});
+                    file_off += res.n_bytes; writes_pending++;
+                    PL.next_to_write = b->id + 1;
+                }
                 PL.cv.notify_all();
             }
         };
-        std::vector<std::thread> th;
+        std::vector<std::thread> th, wr;
+        const int n_writers = std::max(2, std::min(8, nd * 2));
+        for (int i = 0; i < n_writers; i++) wr.emplace_back(writer);
         for (int d = 0; d < nd; d++) th.emplace_back(worker, d);
         for (auto &t : th) t.join();
+        { std::unique_lock<std::mutex> lk(PL.mu); PL.cv.wait(lk, [&] { return writes_pending == 0 || PL.failed; }); workers_done = true; }
+        PL.cv.notify_all();
+        for (auto &t : wr) t.join();
+        PL.cv.notify_all();
         reader.join();
-        fclose(fo);
+        close(out_fd);
         if (PL.failed) return 3;
-        // junction counts summed by key over the GPUs (UpdateGlobalSJMap, Mapping.cpp:567-577); a key's type is the first one seen
-        // in input order: blocks alternate over the devices, so take it from the device that saw the key in the earliest block —
-        // the type of a (g1,g2) pair is a function of the genome (the splice motif), identical wherever it is seen
+        // junction counts summed by key over the GPUs (UpdateGlobalSJMap, Mapping.cpp:567-577); the type of a (g1,g2) pair is a
+        // function of the genome (the splice motif), identical wherever it is seen
         std::map<std::pair<int64_t, int64_t>, std::pair<int, int>> all;
         for (int d = 0; d < nd; d++)
             for (auto &kv : sj[d]) { auto it = all.find(kv.first); if (it != all.end()) it->second.second += kv.second.second; else all[kv.first] = kv.second; }
