@@ -36,7 +36,7 @@ MIS = os.environ.get("DART_BENCH_MIS")  # None = as BASELINE names the config (n
 # fits L2 — used for the HBM-bound roofline of k_search in profiles/, never for the headline line.
 CONTEXTS = int(os.environ.get("DART_BENCH_CONTEXTS", 4))   # batches in flight per GPU (one context each, one host thread for all)
 PARTS = int(os.environ.get("DART_BENCH_PARTS", 2))         # sub-batches a step's batch is cut into
-NW_OPS_PER_CELL = 22   # integer instructions of the recurrence + traceback flags per cell in k_nw_thread's inner loop (SASS listing in profiles/)
+NW_OPS_PER_CELL = 26   # SASS instructions per cell in k_nw_thread's inner loop (4 cells per iteration; listing: profiles/r02_nw_thread_sass.txt)
 WORKLOAD = os.environ.get("DART_BENCH_WORKLOAD", "c2")
 SCALE = float(os.environ.get("DART_BENCH_SCALE", "0.06"))
 

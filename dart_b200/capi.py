@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdartgpu.so")
+LIB_PATH = os.environ.get("DARTGPU_LIB", os.path.join(HERE, "libdartgpu.so"))   # DARTGPU_LIB: A/B runs of two builds
 
 
 class DartGpuError(RuntimeError):

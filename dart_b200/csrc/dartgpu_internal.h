@@ -83,6 +83,8 @@ struct BatchCtl {
     unsigned long long nw_ops[2], nw_flags[2], nw_aux[2];   // pool use of the two NW rounds (B: gap flanks, C: non-simple pairs)
     int32_t nk, nw_jobs[2], nw_small[2];                    // job-queue lengths; jobs of the thread-per-alignment class
     int32_t nw_max_n[2];
+    int32_t phase_queue[3];                                 // candidates waiting for the repair phases B, C, D (report_kernels.cu)
+    int32_t pad0;
     int32_t abort;                                          // CAP_* bits: a capacity was exceeded, the batch must be re-run
     int32_t err;                                            // ERR_* bits: internal invariants that must never fire
     uint32_t steal, big_count, mid_count, heavy_count;    // work-stealing / queue counters of the seeding and 8-mer kernels
@@ -202,8 +204,11 @@ void launch_scan_u32_to_i64(const uint32_t *in, int64_t *out, int n, void *tmp, 
 // nw_kernel.cu
 struct NwJobDev { int64_t s1_off; int64_t gpos; int64_t op_off; int64_t flag_off; int64_t aux_off; int32_t m, n; };
 constexpr int NW_BINS = 64 * 64 + 1;   // shape classes (n, m) of the thread-per-alignment kernel + one for everything larger
+struct NwSorted { int64_t s1_off, gpos, op_off; int32_t job; int16_t m, n; };   // a job as the thread-per-alignment kernel reads it: 32 bytes
 struct NwScratch {         // shape-class counting sort of the job queue, owned by the context
     DevBuf<uint32_t> hist, bin_start, bin_cur, order, counter;   // hist and counter are left zeroed by k_nw_bins / the kernels that use them
+    DevBuf<NwSorted> sorted;
+    DevBuf<uint32_t> gflags;                                     // per-warp traceback-flag scratch of the shapes whose flags do not fit on chip
 };
 struct NwRound {           // one batched NW launch over a job queue whose length lives on the device
     NwJobDev *jobs; const int32_t *n_jobs; int cap_jobs;

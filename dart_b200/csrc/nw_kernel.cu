@@ -199,7 +199,7 @@ k_nw_prepare(NwJobDev *__restrict__ jobs, int cap_jobs, int round, int with_aux,
         if (j < n_jobs) {
             m = jobs[j].m; n = jobs[j].n;
             so = (unsigned)(max(m, 0) + max(n, 0));
-            sf = (m > 0 && n > 0) ? (unsigned)(m * ((n + 15) >> 4)) : 0u;
+            sf = (m > 0 && n > 0 && !nw_thread_class(m, n)) ? (unsigned)(m * ((n + 15) >> 4)) : 0u;   // the thread class keeps its flags on chip
             sa = (with_aux && !(j & 1)) ? (unsigned)(2 * (max(m, 0) + 1)) : 0u;
             bin = nw_bin(m, n);
             if (m > 0 && n > 0) cells += (unsigned long long)m * n;
@@ -258,7 +258,7 @@ k_nw_bins(uint32_t *__restrict__ hist, uint32_t *__restrict__ bin_start, uint32_
 // order[] = job ids grouped by bin; the lanes of a warp that hold jobs of the same bin share one atomic
 __global__ void __launch_bounds__(256)
 k_nw_scatter(const NwJobDev *__restrict__ jobs, int cap_jobs, int round, uint32_t *__restrict__ bin_cur, uint32_t *__restrict__ order,
-             const BatchCtl *__restrict__ ctl)
+             NwSorted *__restrict__ sorted, const BatchCtl *__restrict__ ctl)
 {
     if (ctl->abort) return;
     const int n_jobs = min(ctl->nw_jobs[round], cap_jobs);
@@ -272,84 +272,154 @@ k_nw_scatter(const NwJobDev *__restrict__ jobs, int cap_jobs, int round, uint32_
         unsigned base = 0;
         if (valid && lane == leader) base = atomicAdd(&bin_cur[bin], (unsigned)__popc(peers));
         base = __shfl_sync(FULLM, base, leader);
-        if (valid) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)j;
+        if (valid) {
+            const unsigned at = base + __popc(peers & ((1u << lane) - 1u));
+            order[at] = (uint32_t)j;
+            const NwJobDev J = jobs[j];
+            NwSorted d; d.s1_off = J.s1_off; d.gpos = J.gpos; d.op_off = J.op_off; d.job = j; d.m = (int16_t)min(J.m, 32767); d.n = (int16_t)min(J.n, 32767);
+            sorted[at] = d;           // the thread-per-alignment kernel reads its 32 descriptors as one coalesced kilobyte
+        }
     }
 }
 
+// ---- the thread-per-alignment kernel, second version ----
+// Round-1 ncu of the first version: warps active 21-26 % (33 KB of static shared rows per CTA), ~45 SASS instructions per
+// cell, every traceback flag word stored to and re-loaded from the job's own slice of global memory (32 sectors per warp
+// store), n calls of a bounds-checked single-base load for the genome window.  This version:
+//   * a warp owns a 2048-word slice of shared memory and gives each of its alignments what its shape needs — one word per
+//     column for the previous row (S in the low half, the NEXT row's T in the high half, both int16) plus m x ceil(n/16)
+//     words of traceback flags — laid out [word][lane]; shapes that need more than 64 words per alignment run fewer lanes
+//     per pass (a 64 x 64 alignment needs 321 words: 6 lanes), the small shapes that make up almost every batch run all 32;
+//   * no traceback flag touches global memory; the walk back is a chain of shared-memory loads;
+//   * the recurrence is DPX (max(a + b, c) and three-way max are one instruction each on sm_100), four columns per loop
+//     iteration with immediate flag masks; the row's match mask comes from two bit-plane words of the genome window
+//     (built once per alignment from three aligned loads), not from a per-cell compare of extracted bases;
+//   * job descriptors arrive sorted and compact (k_nw_scatter), 32 bytes per lane, coalesced.
+// Cells right of column n inside the last group of four are computed and ignored: nothing to their left depends on them.
+constexpr int NWT_SLICE = 2112;           // shared-memory words per warp: 66 per lane = the rows of the widest alignment (4 * 16 + 1)
+constexpr int NWT_FLAG_WORDS = 256;       // global flag scratch per lane for the shapes whose flags do not fit: 64 rows x 4 words
+
+__device__ __forceinline__ uint32_t even_bits16(uint32_t y)
+{   // bits 0,2,4,..,30 of y -> bits 0..15
+    y &= 0x55555555u;
+    y = (y | (y >> 1)) & 0x33333333u;
+    y = (y | (y >> 2)) & 0x0F0F0F0Fu;
+    y = (y | (y >> 4)) & 0x00FF00FFu;
+    return (y | (y >> 8)) & 0x0000FFFFu;
+}
+
 __global__ void __launch_bounds__(NWT_THREADS)
-k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwJobDev *__restrict__ jobs, const uint32_t *__restrict__ order,
-            const BatchCtl *__restrict__ ctl, int round, uint32_t *next_chunk, uint32_t *flags, uint8_t *ops, int32_t *nops)
+k_nw_thread(DevIndex ix, const uint8_t *__restrict__ codes, const NwSorted *__restrict__ sorted, const BatchCtl *__restrict__ ctl, int round,
+            uint32_t *next_chunk, uint32_t *__restrict__ gflags, uint8_t *ops, int32_t *nops)
 {
     if (ctl->abort) return;
-    __shared__ int16_t sS[NWT_MAX + 1][NWT_THREADS], sT[NWT_MAX + 1][NWT_THREADS];
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_all[NWT_THREADS / 32][NWT_SLICE];
+    const int lane = threadIdx.x & 31;
+    uint32_t *sm = s_all[threadIdx.x >> 5];
+    // this warp's flag scratch in global memory, laid out [word][lane] like the shared slice: a warp's store of one flag word
+    // is one 128-byte line (the first version's per-job slices cost 32 sectors per store), its loads stay in L1 / L2
+    uint32_t *gw = gflags + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 * NWT_FLAG_WORDS);
     const int n_jobs = ctl->nw_small[round];              // the shape-sorted jobs of this class come first
     const int n_chunks = (n_jobs + 31) / 32;
     // chunks of 32 shape-sorted jobs are handed out dynamically to the WARPS, the largest shapes first, so that the grid
-    // finishes together (with a static stride the CTAs that drew the chunks of 60 x 60 jobs ran long after the others on
-    // the bench's 250 k-job launches; a hand-out per CTA with a barrier made the warps of a CTA wait for each other)
+    // finishes together
     for (;;) {
         int chunk = 0;
-        if ((tid & 31) == 0) chunk = (int)atomicAdd(next_chunk, 1u);
+        if (lane == 0) chunk = (int)atomicAdd(next_chunk, 1u);
         chunk = __shfl_sync(FULLM, chunk, 0);
         if (chunk >= n_chunks) break;
-        const int k = (n_chunks - 1 - chunk) * 32 + (tid & 31);
-        if (k >= n_jobs) continue;
-        const int job = (int)order[k];
-        const NwJobDev J = jobs[job];
-        const int m = J.m, n = J.n;
-        // genome bases of the job: base j-1 at bits 2(j-1) of g0 (j <= 32) / g1
-        uint64_t g0 = 0, g1 = 0;
-        for (int j = 0; j < n; j++) {
-            const uint64_t b = (uint64_t)ref_base(ix, J.gpos + j);
-            if (j < 32) g0 |= b << (2 * j); else g1 |= b << (2 * (j - 32));
-        }
-        for (int j = 0; j <= n; j++) { sS[j][tid] = (int16_t)(j == 0 ? 0 : -2 - j); sT[j][tid] = (int16_t)NWT_NEG; }
-        const int wpr = (n + 15) >> 4;
-        uint32_t *fl = flags + J.flag_off;
-        const uint8_t *s1 = codes + J.s1_off;
-        for (int i = 1; i <= m; i++) {
-            int a = (int)s1[i - 1];
-            a = (a & 4) ? 7 : (a & 3);
-            int Sl = -2 - i, Rl = NWT_NEG, Sd = sS[0][tid];
-            sS[0][tid] = (int16_t)Sl;
-            // 16 columns at a time: their genome bases in one 32-bit word (shifted out two bits per column), their
-            // traceback flags in another (shifted in), one store per group
-            for (int jg = 0; jg < wpr; jg++) {
-                uint32_t gw = jg == 0 ? (uint32_t)g0 : jg == 1 ? (uint32_t)(g0 >> 32) : jg == 2 ? (uint32_t)g1 : (uint32_t)(g1 >> 32);
-                uint32_t fw = 0;
-                const int j0 = 16 * jg + 1, cols = min(16, n - 16 * jg);
-                for (int c = 0; c < cols; c++) {
-                    const int j = j0 + c;
-                    const int Su = sS[j][tid], Tu = sT[j][tid];
-                    const int b = (int)(gw & 3u);
-                    gw >>= 2;
-                    const int R = max(Rl - 1, Sl - 3);
-                    const int T = max(Tu - 1, Su - 3);
-                    const int h = max(Sd + (a == b ? 3 : -3), max(R, T));
-                    const int S = (h / 2) * 2;
-                    fw |= ((S == R ? 1u : 0u) | (S == T ? 2u : 0u)) << (2 * c);
-                    Sd = Su; Sl = S; Rl = R;
-                    sS[j][tid] = (int16_t)S; sT[j][tid] = (int16_t)T;
+        const int k0 = (n_chunks - 1 - chunk) * 32;
+        NwSorted J{};
+        if (k0 + lane < n_jobs) J = sorted[k0 + lane];
+        const int cnt = min(32, n_jobs - k0);
+        // words per alignment of this chunk: rows + flags in the shared slice when 32 alignments fit (66 words each); otherwise
+        // only the rows stay on chip and the flags go to the warp's global scratch.  Either way all 32 lanes run.
+        const int my_need = k0 + lane < n_jobs ? (4 * ((J.n + 3) >> 2) + 1) + J.m * ((J.n + 15) >> 4) : 0;
+        const int need = __reduce_max_sync(FULLM, my_need);
+        const bool flags_on_chip = need * 32 <= NWT_SLICE;
+        constexpr int lpp = 32;
+        for (int p0 = 0; p0 < cnt; p0 += lpp) {
+            __syncwarp();
+            // the alignment of this lane in this pass
+            const int src = p0 + lane;
+            const bool on = lane < lpp && src < cnt;
+            NwSorted A;
+            A.s1_off = __shfl_sync(FULLM, J.s1_off, src & 31); A.gpos = __shfl_sync(FULLM, J.gpos, src & 31);
+            A.op_off = __shfl_sync(FULLM, J.op_off, src & 31); A.job = __shfl_sync(FULLM, J.job, src & 31);
+            const int mn = __shfl_sync(FULLM, (int)(uint16_t)J.m | (int)J.n << 16, src & 31);
+            if (!on) continue;
+            const int m = mn & 0xFFFF, n = mn >> 16;
+            const int wpr = (n + 15) >> 4, n4 = (n + 3) >> 2;
+            uint32_t *row = sm + lane;                               // row[j] at row[j * lpp]
+            uint32_t *flg = flags_on_chip ? sm + (4 * n4 + 1) * lpp + lane : gw + lane;   // flag word w at flg[w * lpp]
+            // ---- genome window -> bit planes (bit j = low / high bit of base j) ----
+            uint64_t glo = 0, ghi = 0;
+            if (A.gpos >= 0 && A.gpos + 80 <= 2 * ix.G) {
+                const uint32_t *w = ix.ref2 + (A.gpos >> 4);
+                const int sh = 2 * (int)(A.gpos & 15);
+                uint32_t prev = __ldg(w);
+                for (int q = 0; q < wpr; q++) {
+                    const uint32_t nxt = __ldg(w + q + 1);
+                    const uint32_t x = __funnelshift_l(nxt, prev, sh);   // 16 bases, the first in the top bits
+                    const uint32_t y = __brev(x);                         // base k: high bit at 2k, low bit at 2k+1
+                    ghi |= (uint64_t)even_bits16(y) << (16 * q);
+                    glo |= (uint64_t)even_bits16(y >> 1) << (16 * q);
+                    prev = nxt;
                 }
-                fl[(size_t)(i - 1) * wpr + jg] = fw;
+            } else {
+                for (int j = 0; j < n; j++) { const uint64_t b = (uint64_t)ref_base(ix, A.gpos + j); glo |= (b & 1) << j; ghi |= (b >> 1) << j; }
             }
-        }
-        int ti = m, tj = n, cnt = 0;
-        int64_t pos = J.op_off + m + n;
-        while (ti > 0 || tj > 0) {
-            int op;
-            if (ti == 0) op = 1;
-            else if (tj == 0) op = 2;
-            else {
-                const uint32_t f = (fl[(size_t)(ti - 1) * wpr + ((tj - 1) >> 4)] >> (((tj - 1) & 15) * 2)) & 3u;
-                op = (f & 1u) ? 1 : ((f & 2u) ? 2 : 0);
+            // ---- row 0: S[0][j] = -2 - j; the T of row 1 = max(-inf - 1, S[0][j] - 3) = -5 - j ----
+            for (int j = 1; j <= 4 * n4; j++) row[j * lpp] = (uint32_t)((-2 - j) & 0xFFFF) | (uint32_t)(-5 - j) << 16;
+            const uint8_t *s1 = codes + A.s1_off;
+            for (int i = 1; i <= m; i++) {
+                const int a = (int)s1[i - 1];
+                // columns whose genome base equals the read base of this row (codes 8..11 are lower-case ACGT; bit 2 = not ACGT)
+                const uint64_t alo = (a & 1) ? ~0ull : 0ull, ahi = (a & 2) ? ~0ull : 0ull;
+                uint64_t eq = (a & 4) ? 0ull : ~((glo ^ alo) | (ghi ^ ahi));
+                int Sl = -2 - i, Rn = NWT_NEG, Sd = i == 1 ? 0 : -1 - i;      // S[i][0], R[i][1] before its max, S[i-1][0]
+                uint32_t fw = 0;
+                uint32_t *rp = row + lpp, *fp = flg + (i - 1) * wpr * lpp;
+                for (int g = 0; g < n4; g++) {
+                    const uint32_t e4 = (uint32_t)eq & 15u;
+                    eq >>= 4;
+                    uint32_t f8 = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t wv = rp[c * lpp];
+                        const int Su = (int)(int16_t)(wv & 0xFFFFu), T = (int)wv >> 16;
+                        const int R = __viaddmax_s32(Rn, -1, Sl - 3);
+                        const int d = Sd + ((e4 & (1u << c)) ? 3 : -3);
+                        const int h = __vimax3_s32(d, R, T);
+                        const int S = (h + (int)((uint32_t)h >> 31)) & ~1;          // (h / 2) * 2, truncating toward zero
+                        if (S == R) f8 |= 1u << (2 * c);
+                        if (S == T) f8 |= 2u << (2 * c);
+                        const int Tn = __viaddmax_s32(T, -1, S - 3);
+                        rp[c * lpp] = (uint32_t)(S & 0xFFFF) | (uint32_t)Tn << 16;
+                        Sd = Su; Sl = S; Rn = R;
+                    }
+                    rp += 4 * lpp;
+                    fw |= f8 << (8 * (g & 3));
+                    if ((g & 3) == 3 || g == n4 - 1) { *fp = fw; fp += lpp; fw = 0; }
+                }
             }
-            ops[--pos] = (uint8_t)op;
-            cnt++;
-            if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
+            // ---- traceback (nw_alignment.cpp:61-74): S == R first (gap in the read string), then S == T, else diagonal ----
+            int ti = m, tj = n, cntc = 0;
+            int64_t pos = A.op_off + m + n;
+            while (ti > 0 || tj > 0) {
+                int op;
+                if (ti == 0) op = 1;
+                else if (tj == 0) op = 2;
+                else {
+                    const uint32_t f = (flg[((ti - 1) * wpr + ((tj - 1) >> 4)) * lpp] >> (((tj - 1) & 15) * 2)) & 3u;
+                    op = (f & 1u) ? 1 : ((f & 2u) ? 2 : 0);
+                }
+                ops[--pos] = (uint8_t)op;
+                cntc++;
+                if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
+            }
+            nops[A.job] = cntc;
         }
-        nops[job] = cnt;
     }
 }
 
@@ -446,13 +516,14 @@ void launch_nw(const DevIndex &ix, const uint8_t *codes, const NwRound &R, Batch
         S.hist.reserve(NW_BINS + 1); S.counter.reserve(4);
         launch_zero(S.hist.p, (NW_BINS + 1) * sizeof(uint32_t), st);
     }
-    S.bin_start.reserve(NW_BINS + 1); S.bin_cur.reserve(NW_BINS + 1); S.order.reserve(R.cap_jobs);
+    S.bin_start.reserve(NW_BINS + 1); S.bin_cur.reserve(NW_BINS + 1); S.order.reserve(R.cap_jobs); S.sorted.reserve(R.cap_jobs);
     int g0 = (R.cap_jobs + 255) / 256; if (g0 > sms * 8) g0 = sms * 8;
     k_nw_prepare<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, R.with_aux, S.hist.p, ctl);
     k_nw_bins<<<1, 1024, 0, st>>>(S.hist.p, S.bin_start.p, S.bin_cur.p, S.counter.p, R.round, R.cap_ops, R.cap_flags, R.cap_aux, ctl);
-    k_nw_scatter<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, S.bin_cur.p, S.order.p, ctl);
-    int gt = (R.cap_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > sms * 6) gt = sms * 6;
-    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, R.jobs, S.order.p, ctl, R.round, S.counter.p, R.flags, R.ops, R.nops);
+    k_nw_scatter<<<g0, 256, 0, st>>>(R.jobs, R.cap_jobs, R.round, S.bin_cur.p, S.order.p, S.sorted.p, ctl);
+    int gt = (R.cap_jobs + NWT_THREADS - 1) / NWT_THREADS; if (gt > sms * 6) gt = sms * 6;      // 6 CTAs of 33 KB shared memory per SM
+    S.gflags.reserve((size_t)gt * (NWT_THREADS / 32) * 32 * NWT_FLAG_WORDS);
+    k_nw_thread<<<gt, NWT_THREADS, 0, st>>>(ix, codes, S.sorted.p, ctl, R.round, S.counter.p, S.gflags.p, R.ops, R.nops);
     // everything larger: a warp per job
     int want = (R.cap_jobs + (NW_THREADS / 32) - 1) / (NW_THREADS / 32);
     int grid = want < sms * 8 ? want : sms * 8;

@@ -37,40 +37,43 @@ __global__ void k_ctl_cands(BatchCtl *ctl, const int64_t *cand_off, const int64_
     if (nc > cap_cands || nr > cap_reps) atomicOr(&ctl->abort, CAP_CANDS);
 }
 
-__global__ void k_cand_init(int n_reads, const int64_t *seed_off, const int64_t *cand_off, const uint32_t *ncand,
-                            const int32_t *cbegin, const int32_t *ccount, const int32_t *cscore, const uint64_t *keys, CandState *cs,
-                            const BatchCtl *ctl)
+// candidate records of a read from the clustering output
+__device__ __forceinline__ void cand_init_read(int r, const int64_t *seed_off, const int64_t *cand_off, const uint32_t *ncand, const int32_t *cbegin,
+                                               const int32_t *ccount, const int32_t *cscore, const uint64_t *keys, CandState *cs)
 {
-    if (ctl->abort) return;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
-        const int64_t so = seed_off[r], co = cand_off[r];
-        const int nc = (int)ncand[r];
-        for (int k = 0; k < nc; k++) {
-            CandState c;
-            c.read = r; c.seed_begin = cbegin[so + k]; c.seed_count = ccount[so + k]; c.Score = cscore[so + k];
-            c.PairedIdx = -1; c.SJtype = -1;
-            uint64_t key = keys[so + c.seed_begin];
-            int64_t pd = key_gpos(key) - key_rpos(key);
-            c.PosDiff = pd < 0 ? 0 : pd;
-            c.pos = 0; c.sv_off = 0; c.cig_off = 0; c.text_off = 0; c.sv_n = 0; c.sv_cap = 0; c.cig_cap = 0; c.cig_n = 0; c.text_len = 0;
-            c.AlnScore = 0; c.mis = 0; c.chr = 0; c.n_ext = 0; c.live = 0; c.skip = 0; c.dir = 0; c.pad = 0;
-            cs[co + k] = c;
-        }
+    const int64_t so = seed_off[r], co = cand_off[r];
+    const int nc = (int)ncand[r];
+    for (int k = 0; k < nc; k++) {
+        CandState c;
+        c.read = r; c.seed_begin = cbegin[so + k]; c.seed_count = ccount[so + k]; c.Score = cscore[so + k];
+        c.PairedIdx = -1; c.SJtype = -1;
+        uint64_t key = keys[so + c.seed_begin];
+        int64_t pd = key_gpos(key) - key_rpos(key);
+        c.PosDiff = pd < 0 ? 0 : pd;
+        c.pos = 0; c.sv_off = 0; c.cig_off = 0; c.text_off = 0; c.sv_n = 0; c.sv_cap = 0; c.cig_cap = 0; c.cig_n = 0; c.text_len = 0;
+        c.AlnScore = 0; c.mis = 0; c.chr = 0; c.n_ext = 0; c.live = 0; c.skip = 0; c.dir = 0; c.pad = 0;
+        cs[co + k] = c;
     }
 }
 
-// candidate pairing / pruning per read (pair), then the seed-pool demand of the survivors (cap[] was zeroed: the prefix sum
-// behind this kernel runs over the candidate table's capacity)
-__global__ void k_pair_prune(int n_units, int paired, const int64_t *cand_off, CandState *cs, uint32_t *cap, int64_t cap_cands, const BatchCtl *ctl)
+// One thread per read (pair): the candidate records, candidate pairing / pruning, then the seed-pool demand of the survivors
+// (zeros behind the candidate count: the prefix sum behind this kernel runs over the candidate table's capacity).
+// Round 2: k_cand_init, k_pair_prune, k_cand_live and k_set_sv_off were four passes over the 104-byte records.
+__global__ void k_pair_prune(int n_units, int paired, const int64_t *seed_off, const int64_t *cand_off, const uint32_t *ncand, const int32_t *cbegin,
+                             const int32_t *ccount, const int32_t *cscore, const uint64_t *keys, CandState *cs, uint32_t *cap, int64_t cap_cands,
+                             const BatchCtl *ctl)
 {
     if (ctl->abort) return;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
         int64_t a, e;
         if (paired) {
+            cand_init_read(2 * u, seed_off, cand_off, ncand, cbegin, ccount, cscore, keys, cs);
+            cand_init_read(2 * u + 1, seed_off, cand_off, ncand, cbegin, ccount, cscore, keys, cs);
             a = cand_off[2 * u]; e = cand_off[2 * u + 2];
             const int64_t b = cand_off[2 * u + 1];
             pair_and_prune(cs + a, (int)(b - a), cs + b, (int)(e - b), true);
         } else {
+            cand_init_read(u, seed_off, cand_off, ncand, cbegin, ccount, cscore, keys, cs);
             a = cand_off[u]; e = cand_off[u + 1];
             pair_and_prune(cs + a, (int)(e - a), nullptr, 0, false);
         }
@@ -97,58 +100,110 @@ __global__ void k_pair_prune(int n_units, int paired, const int64_t *cand_off, C
 // kernel that may run it takes its configuration (5 CTAs per SM, 8 staged seeds); D alone runs 8 CTAs per SM.
 // The candidate count lives on the device (E.ctl->ncand); `slice_off` = the prefix sum that places this phase's pool slices
 // (A: seed pool, D: CIGAR pool).
-template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 3 ? 5 : 8, MIN_CTAS = WHICH == 3 ? 8 : 5; };
-template <int WHICH>
-__global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E, const int64_t *__restrict__ slice_off)
-{
-    if (E.ctl->abort) return;
-    const int64_t ncand = E.ctl->ncand;
-    constexpr int STAGE_SEEDS = PhaseCfg<WHICH>::STAGE;
-    __shared__ RSeed s_slot[TPB * STAGE_SEEDS];
-    for (int64_t cid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cid < ncand; cid += (int64_t)gridDim.x * blockDim.x) {
-        if (WHICH != 0 && WHICH != 3 && E.stage[cid] != WHICH) continue;    // already past this phase
-        CandState c = E.cs[cid];
-        if (WHICH == 0) c.sv_off = slice_off[cid];
-        if (WHICH == 3) c.cig_off = slice_off[cid];
-        if (!c.live) {
-            if (WHICH == 0) E.stage[cid] = 3;
-            if (WHICH == 3) { E.cs[cid].AlnScore = 0; E.cs[cid].cig_n = 0; E.cs[cid].text_len = 0; }
-            continue;
-        }
-        RSeed *g = E.pool + c.sv_off, *sv = g;
-        const bool staged = phase_seed_bound(c, WHICH) <= STAGE_SEEDS;
-        if (staged) {
-            sv = s_slot + threadIdx.x * STAGE_SEEDS;
-            if (WHICH != 0) for (int i = 0; i < c.sv_n; i++) sv[i] = g[i];
-        }
-        int next = WHICH + 1;
-        if (WHICH == 0) {
-            phase_a(E, c, sv);
-            bool waits = false;
-            for (int i = 1; i < c.sv_n; i++) waits |= sv[i].job >= 0;
-            if (!waits && (!staged || phase_seed_bound(c, 1) <= STAGE_SEEDS)) { phase_b(E, c, sv); next = 2; }
-        }
-        if (WHICH == 1) phase_b(E, c, sv);
-        if ((WHICH == 0 && next == 2) || WHICH == 1) {
-            if (c.n_ext == 0 && (!staged || phase_seed_bound(c, 2) <= STAGE_SEEDS)) {
-                Env E2 = E; E2.njobs = E.njobs_c; E2.njob_count = E.njob_count_c;
-                phase_c(E2, c, sv); next = 3;
-            }
-        }
-        if (WHICH == 2) phase_c(E, c, sv);
-        if (WHICH == 3) phase_d(E, c, sv);
-        if (staged) for (int i = 0; i < c.sv_n; i++) g[i] = sv[i];
-        E.cs[cid] = c;
-        if (WHICH != 3) E.stage[cid] = (uint8_t)next;
-    }
+// Phase D (CIGAR pairs, score, coordinates) needs a slice of the CIGAR pool sized by phase C.  Round 1 placed the slices with a
+// prefix sum over all candidates between C and D, so every candidate was loaded and stored once more by a fourth kernel
+// (0.52 ms of a 5 ms step on config[1]).  Now the slice is claimed from a counter in the control block at a point where the
+// whole warp is converged (one atomic per warp), and a candidate whose phase C queued no alignment job runs D in the same
+// thread, right away: on config[1] that is nearly every candidate, and the fourth kernel finds almost nothing left to do.
+__device__ __forceinline__ long long warp_claim(long long *counter, int need)
+{   // all 32 lanes call this together; returns the start of this lane's `need` slots
+    const int lane = threadIdx.x & 31;
+    int incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    long long base = 0;
+    if (lane == 31 && total > 0) base = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(counter), (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - need;
 }
 
-__global__ void k_cig_caps(const CandState *cs, uint32_t *cap, int64_t cap_cands, const BatchCtl *ctl)
+// Candidates that have to wait for a batched launch (8-mer re-seeding, NW of the gap flanks, NW of the non-simple pairs) are
+// appended to the queue of the phase that picks them up again, so that the later phase kernels run full warps over exactly
+// the candidates they have work for (round-2 ncu of k_phase<3> scanning the whole table with a stage marker: 7.8 of 32 lanes
+// active, 26 % of the warp slots occupied).
+struct PhaseQueues { uint32_t *q[3]; };          // candidates waiting for phase 1 (B), 2 (C), 3 (D)
+
+template <int WHICH> struct PhaseCfg { static constexpr int STAGE = 8, MIN_CTAS = 5; };
+template <int WHICH>
+__global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E, const int64_t *__restrict__ slice_off, long long cap_cig, PhaseQueues Q)
 {
-    if (ctl->abort) return;
-    const int64_t ncand = ctl->ncand;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c <= cap_cands; c += (int64_t)gridDim.x * blockDim.x)
-        cap[c] = (c < ncand && cs[c].live && !cs[c].skip) ? (uint32_t)cs[c].cig_cap : 0u;
+    if (E.ctl->abort) return;
+    const int64_t total = WHICH == 0 ? (int64_t)E.ctl->ncand : (int64_t)E.ctl->phase_queue[WHICH - 1];
+    constexpr int STAGE_SEEDS = PhaseCfg<WHICH>::STAGE;
+    __shared__ RSeed s_slot[TPB * STAGE_SEEDS];
+    const int lane = threadIdx.x & 31;
+    // the loop condition is the same for the 32 lanes of a warp (the claims below need all of them)
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx - lane < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        bool run = idx < total;
+        const int64_t cid = !run ? 0 : WHICH == 0 ? idx : (int64_t)Q.q[WHICH == 0 ? 0 : WHICH - 1][idx];
+        CandState c{};
+        if (run) {
+            c = E.cs[cid];
+            if (WHICH == 0) c.sv_off = slice_off[cid];
+            if (!c.live) {                                                      // pruned candidates only exist in phase A's pass
+                E.cs[cid].AlnScore = 0; E.cs[cid].cig_n = 0; E.cs[cid].text_len = 0;
+                run = false;
+            }
+        }
+        RSeed *g = E.pool + c.sv_off, *sv = g;
+        bool staged = false, want_d = false;
+        int next = WHICH + 1;
+        if (run) {
+            staged = phase_seed_bound(c, WHICH) <= STAGE_SEEDS;
+            if (staged) {
+                sv = s_slot + threadIdx.x * STAGE_SEEDS;
+                if (WHICH != 0) for (int i = 0; i < c.sv_n; i++) sv[i] = g[i];
+            }
+            if (WHICH == 0) {
+                phase_a(E, c, sv);
+                bool waits = false;
+                for (int i = 1; i < c.sv_n; i++) waits |= sv[i].job >= 0;
+                if (!waits && (!staged || phase_seed_bound(c, 1) <= STAGE_SEEDS)) { phase_b(E, c, sv); next = 2; }
+            }
+            if (WHICH == 1) phase_b(E, c, sv);
+            if ((WHICH == 0 && next == 2) || WHICH == 1) {
+                if (c.n_ext == 0 && (!staged || phase_seed_bound(c, 2) <= STAGE_SEEDS)) {
+                    Env E2 = E; E2.njobs = E.njobs_c; E2.njob_count = E.njob_count_c;
+                    phase_c(E2, c, sv); next = 3;
+                }
+            }
+            if (WHICH == 2) { phase_c(E, c, sv); next = 3; }
+            if (WHICH == 3) want_d = true;
+            else if (next == 3) {                   // C just ran: D can follow at once unless C queued an alignment
+                bool waits = false;
+                for (int i = 0; i < c.sv_n; i++) waits |= sv[i].job >= 0;
+                want_d = !waits;
+            }
+        }
+        // ---- the whole warp: claim the CIGAR slices of the candidates that run D now ----
+        __syncwarp();
+        const int need = (want_d && !c.skip) ? c.cig_cap : 0;
+        const long long off = warp_claim(&E.ctl->cig_total, need);
+        if (want_d) {
+            c.cig_off = off;
+            if (off + need > cap_cig) { atomicOr(&E.ctl->abort, CAP_CIG); c.cig_cap = 0; }     // the batch is re-run with a bigger pool
+            phase_d(E, c, sv);
+            next = 4;
+        }
+        if (run) {
+            if (staged) for (int i = 0; i < c.sv_n; i++) g[i] = sv[i];
+            E.cs[cid] = c;
+        }
+        // ---- the whole warp: queue the candidates that wait for a batched launch ----
+        __syncwarp();
+#pragma unroll
+        for (int p = WHICH + 1; p <= 3; p++) {
+            const unsigned m = __ballot_sync(0xffffffffu, run && next == p);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&E.ctl->phase_queue[p - 1], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (run && next == p) Q.q[p - 1][base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)cid;
+            }
+        }
+    }
 }
 
 // ---- final pass ----
@@ -235,7 +290,7 @@ struct DevicePipe {
     DevBuf<uint32_t> u32_a, u32_b, text_len, njunc;
     DevBuf<CandState> cs;
     DevBuf<RSeed> pool;
-    DevBuf<uint8_t> stage;
+    DevBuf<uint32_t> queue;                  // candidates waiting for phases B, C, D
     DevBuf<KmerJobDev> kjobs;
     DevBuf<dartgpu_kmer_hit> khits;
     DevBuf<NwJobDev> jobsB, jobsC;
@@ -324,11 +379,10 @@ void enqueue_pipeline(dartgpu_ctx *c)
     scan_u32(c, D, D->u32_b.p, D->rep_off.p, n);
     k_ctl_cands<<<1, 1, 0, st>>>(ctl, D->cand_off.p, D->rep_off.p, n, cap_c, cap_r);
     D->cs.reserve(cap_c + 1);
-    k_cand_init<<<grid_for(n), TPB, 0, st>>>(n, c->d_seed_off.p, D->cand_off.p, c->d_ncand.p, c->d_cand_begin.p, c->d_cand_count.p,
-                                             c->d_cand_score.p, c->d_keys.p, D->cs.p, ctl);
     // ---- pairing / pruning; seed-pool slices of the survivors (prefix sum over the table's capacity, zeros behind the count) ----
     D->u32_a.reserve(cap_c + 2); D->sv_off.reserve(cap_c + 2);
-    k_pair_prune<<<grid_for(units), TPB, 0, st>>>(units, paired, D->cand_off.p, D->cs.p, D->u32_a.p, cap_c, ctl);
+    k_pair_prune<<<grid_for(units), TPB, 0, st>>>(units, paired, c->d_seed_off.p, D->cand_off.p, c->d_ncand.p, c->d_cand_begin.p, c->d_cand_count.p,
+                                                  c->d_cand_score.p, c->d_keys.p, D->cs.p, D->u32_a.p, cap_c, ctl);
     scan_u32(c, D, D->u32_a.p, D->sv_off.p, cap_c);
     launch_ctl_check(ctl, &ctl->pool_total, D->sv_off.p + cap_c, K.pool, CAP_POOL, st);
     D->pool.reserve(K.pool + 1);
@@ -336,7 +390,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
     const int cap_k = (int)std::min<int64_t>(K.pool / 12 + 2, INT32_MAX / 2), cap_B = (int)std::min<int64_t>(K.pool / 3 + 4, INT32_MAX / 2),
               cap_C = (int)std::min<int64_t>(K.pool + 4, INT32_MAX / 2);
     D->kjobs.reserve(cap_k); D->khits.reserve(cap_k); D->jobsB.reserve(cap_B); D->jobsC.reserve(cap_C);
-    c->stats.kernel_launches += 10;
+    c->stats.kernel_launches += 9;
 
     Env E{};
     E.P = PhaseParams{P.max_gaps, P.max_intron, P.min_intron, P.max_mismatch, P.multi_hit, P.pair_end, P.all_sj};
@@ -348,11 +402,13 @@ void enqueue_pipeline(dartgpu_ctx *c)
     E.kjobs = D->kjobs.p; E.kjob_count = &ctl->nk; E.khits = D->khits.p;
     E.njobs = D->jobsB.p; E.njob_count = &ctl->nw_jobs[0];          // phase B's queue (also used by candidates fast-tracked out of A)
     E.njobs_c = D->jobsC.p; E.njob_count_c = &ctl->nw_jobs[1];      // phase C's queue
-    D->stage.reserve(cap_c + 1);             // written for every candidate by phase A
-    E.stage = D->stage.p;
+    D->queue.reserve(3 * (size_t)(cap_c + 1));
+    PhaseQueues Q{{D->queue.p, D->queue.p + (cap_c + 1), D->queue.p + 2 * (cap_c + 1)}};
+    D->cig.reserve(K.cig + 1);
+    E.cig = D->cig.p;
 
-    // ---- phase A -> 8-mer re-seeding ----
-    k_phase<0><<<grid_for(cap_c), TPB, 0, st>>>(E, D->sv_off.p);
+    // ---- phase A -> 8-mer re-seeding (candidates with nothing to repair run B, C and D in the same pass) ----
+    k_phase<0><<<grid_for(cap_c), TPB, 0, st>>>(E, D->sv_off.p, K.cig, Q);
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaEventRecord(c->ev[8], st));
     launch_kmer(c->ix, c->d_codes.p, D->kjobs.p, &ctl->nk, cap_k, std::max(c->max_rlen, 8), D->khits.p, c->kscratch, ctl, K.krecs, st);
@@ -361,25 +417,20 @@ void enqueue_pipeline(dartgpu_ctx *c)
     c->stats.kernel_launches += 1 + KMER_LAUNCHES;
 
     // ---- phase B -> NW of every gap against both flanks ----
-    k_phase<1><<<grid_for(cap_c), TPB, 0, st>>>(E, nullptr);
+    k_phase<1><<<grid_for(cap_c), TPB, 0, st>>>(E, nullptr, K.cig, Q);
     DG_CUDA(cudaGetLastError());
     nw_round(c, D, 0, D->jobsB.p, cap_B, D->opsB, D->nopsB);
 
     // ---- phase C -> NW of every non-simple pair ----
     E.ops = D->opsB.p; E.nops = D->nopsB.p; E.done_jobs = D->jobsB.p; E.xscratch = D->aux.p;
     E.njobs = D->jobsC.p; E.njob_count = &ctl->nw_jobs[1];
-    k_phase<2><<<grid_for(cap_c), TPB, 0, st>>>(E, nullptr);
+    k_phase<2><<<grid_for(cap_c), TPB, 0, st>>>(E, nullptr, K.cig, Q);
     DG_CUDA(cudaGetLastError());
     nw_round(c, D, 1, D->jobsC.p, cap_C, D->opsC, D->nopsC);
 
-    // ---- phase D: CIGAR pairs, score, coordinates ----
-    D->cig_off.reserve(cap_c + 2);
-    k_cig_caps<<<grid_for(cap_c + 1), TPB, 0, st>>>(D->cs.p, D->u32_a.p, cap_c, ctl);
-    scan_u32(c, D, D->u32_a.p, D->cig_off.p, cap_c);
-    launch_ctl_check(ctl, &ctl->cig_total, D->cig_off.p + cap_c, K.cig, CAP_CIG, st);
-    D->cig.reserve(K.cig + 1);
-    E.ops = D->opsC.p; E.nops = D->nopsC.p; E.done_jobs = D->jobsC.p; E.cig = D->cig.p;
-    k_phase<3><<<grid_for(cap_c), TPB, 0, st>>>(E, D->cig_off.p);
+    // ---- phase D for the candidates that waited for an alignment: CIGAR pairs, score, coordinates ----
+    E.ops = D->opsC.p; E.nops = D->nopsC.p; E.done_jobs = D->jobsC.p;
+    k_phase<3><<<grid_for(cap_c), TPB, 0, st>>>(E, nullptr, K.cig, Q);
     DG_CUDA(cudaGetLastError());
 
     // ---- per read / pair: best, mate rescue, flags, MAPQ; record layout (prefix sums over the reads) ----
@@ -393,7 +444,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
     D->text.reserve(K.text + 1); D->junc.reserve(K.junc + 1);
     k_write_records<<<grid_for(n), TPB, 0, st>>>(E, n, D->cand_off.p, D->rr.p, D->rep.p, D->text_off.p, D->text.p, D->junc_off.p, D->junc.p);
     DG_CUDA(cudaGetLastError());
-    c->stats.kernel_launches += 14;
+    c->stats.kernel_launches += 10;
     auto predict = [&](int64_t last, int64_t cap, int64_t first_guess) {
         int64_t want = last < 0 ? first_guess : (int64_t)((double)last * (double)n / std::max(1, D->last_n) * 1.02) + 4096;
         return std::max<int64_t>(0, std::min(want, cap));

@@ -127,7 +127,6 @@ struct Env {
     KmerJobDev *kjobs; int32_t *kjob_count; const dartgpu_kmer_hit *khits;
     NwJobDev *njobs; int32_t *njob_count;       // queue of the phase that runs (B: gap pairs, C: non-simple pairs)
     NwJobDev *njobs_c; int32_t *njob_count_c;    // phase C's queue, for candidates that run A-B-C in one go
-    uint8_t *stage;                              // per candidate: the next phase it has to run (device kernels only)
     const uint8_t *ops; const int32_t *nops;     // NW results of the round being consumed (right-aligned per job)
     const NwJobDev *done_jobs;                   // the jobs those results belong to
     int32_t *xscratch;                           // Rvec/Lvec scratch of the gap-extension jobs
@@ -586,6 +585,68 @@ HD bool simple_enough(const Env &E, const uint8_t *rc, const RSeed &sp, int *n_o
     return nm <= 2 && nm <= (int)(sp.rLen * 0.2);
 }
 
+// nw_alignment (nw_alignment.cpp:18-82) for blocks of at most NW_TINY x NW_TINY, in the calling thread: the integer half-unit
+// recurrence and the traceback priority of nw_kernel.cu (S == R first, then S == T, else diagonal), flags in two 64-bit
+// registers.  On BASELINE config[1] half of all candidates carry exactly one non-simple pair of a base or two (a mismatch
+// between two exact seeds fails the "<= 2 mismatches and <= 20 %" shortcut of tools.cpp:149 when the block is shorter than 5
+// bases): round 1 sent a million 1..10-cell alignments per batch through the job queue, the shape sort and the NW kernel, and
+// every one of those candidates through one more pass of the phase kernels.  They are now aligned where they are needed.
+// ops: columns left to right (0 both advance, 1 gap in the read string, 2 gap in the genome string); returns their number.
+constexpr int NW_TINY = 8;
+constexpr int JOB_NONE = -1, JOB_TINY = -2;
+HDN int nw_tiny(const Env &E, const uint8_t *s1, int m, int64_t gpos, int n, uint8_t *ops)
+{
+    if (m <= 0 || n <= 0) {                       // one empty side: all gaps (nw_alignment.cpp:61-74 with i or j at 0)
+        const int k = (m > 0 ? m : 0) + (n > 0 ? n : 0);
+        for (int t = 0; t < k; t++) ops[t] = (uint8_t)(m <= 0 ? 1 : 2);
+        return k;
+    }
+    constexpr int NEG = -30000;
+    int g[NW_TINY], S[NW_TINY + 1], T[NW_TINY + 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < NW_TINY; j++) { g[j] = j < n ? E.ref.code(gpos + j) : 0; S[j + 1] = -3 - j; T[j + 1] = NEG; }
+    S[0] = 0; T[0] = NEG;
+    uint64_t fR = 0, fT = 0;                      // cell (i, j) at bit (i - 1) * 8 + (j - 1)
+    for (int i = 1; i <= m; i++) {
+        int a = (int)s1[i - 1];
+        a = (a & 4) ? 7 : (a & 3);                // 8..11 are lower-case ACGT: same base for the table compare
+        int Sl = -2 - i, Rl = NEG, Sd = S[0];
+        S[0] = Sl;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 1; j <= NW_TINY; j++) {
+            if (j <= n) {
+                const int Su = S[j], Tu = T[j];
+                const int R = (Rl - 1 > Sl - 3) ? Rl - 1 : Sl - 3;
+                const int Tt = (Tu - 1 > Su - 3) ? Tu - 1 : Su - 3;
+                int h = Sd + (a == g[j - 1] ? 3 : -3);
+                if (R > h) h = R;
+                if (Tt > h) h = Tt;
+                const int Sc = (h / 2) * 2;       // the reference's max(short, short, short) truncates toward zero
+                const int bit = (i - 1) * 8 + (j - 1);
+                if (Sc == R) fR |= 1ull << bit;
+                if (Sc == Tt) fT |= 1ull << bit;
+                Sd = Su; Sl = Sc; Rl = R; S[j] = Sc; T[j] = Tt;
+            }
+        }
+    }
+    uint8_t rev[2 * NW_TINY];
+    int ti = m, tj = n, k = 0;
+    while (ti > 0 || tj > 0) {
+        int op;
+        if (ti == 0) op = 1;
+        else if (tj == 0) op = 2;
+        else { const int bit = (ti - 1) * 8 + (tj - 1); op = ((fR >> bit) & 1) ? 1 : (((fT >> bit) & 1) ? 2 : 0); }
+        rev[k++] = (uint8_t)op;
+        if (op == 1) tj--; else if (op == 2) ti--; else { ti--; tj--; }
+    }
+    for (int t = 0; t < k; t++) ops[t] = rev[k - 1 - t];
+    return k;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // phase C: gapped partitions -> seeds, splice-motif snapping, normal pairs, pair alignments to run
 // ---------------------------------------------------------------------------------------------------
@@ -632,11 +693,12 @@ HDN void phase_c(const Env &E, CandState &c, RSeed *sv)
         if (middle && (sp.PosDiff == -1 || sp.rLen == 0 || sp.gLen == 0)) continue;
         int nm;
         if (simple_enough(E, rc, sp, &nm)) continue;
+        cap += sp.rLen + sp.gLen + 2;
+        if (sp.rLen <= NW_TINY && sp.gLen <= NW_TINY) { sp.job = JOB_TINY; continue; }       // aligned in place by phase D (nw_tiny)
         int id = alloc_slots(E.njob_count, 1);
         NwJobDev a; a.s1_off = coff + sp.rPos; a.gpos = sp.gPos; a.op_off = 0; a.flag_off = 0; a.aux_off = 0; a.m = sp.rLen; a.n = sp.gLen;
         E.njobs[id] = a;
         sp.job = id;
-        cap += sp.rLen + sp.gLen + 2;
     }
     c.cig_cap = cap;
 }
@@ -707,13 +769,16 @@ HDN void phase_d(const Env &E, CandState &c, RSeed *sv)
         if (!head && !tail && sp.PosDiff == -1) cv.push(sp.rLen, 'S');
         else if (!head && !tail && (sp.rLen == 0 || sp.gLen == 0)) {
             if (sp.rLen > 0) cv.push(sp.rLen, 'I'); else if (sp.gLen > 0) cv.push(sp.gLen, 'D');
-        } else if (sp.job < 0) {
+        } else if (sp.job == JOB_NONE) {
             int nm = 0;
             simple_enough(E, rc, sp, &nm);
             score = sp.rLen - nm;
             cv.push(sp.rLen, 'M');
         } else {
-            const Aln A = job_alignment(E, sp.job);
+            uint8_t tiny_ops[2 * NW_TINY];
+            Aln A;
+            if (sp.job == JOB_TINY) { A.k = nw_tiny(E, rc + sp.rPos, sp.rLen, sp.gPos, sp.gLen, tiny_ops); A.ops = tiny_ops; }
+            else A = job_alignment(E, sp.job);
             const uint8_t *s1 = rc + sp.rPos;
             const int64_t g0 = sp.gPos;
             if (!head && !tail) score = add_cigar(E, s1, g0, A, 0, A.k, 0, g0, cv);
