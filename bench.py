@@ -187,6 +187,57 @@ def hotpath_baseline(g, idx, cores):
                       "reads pre-parsed in memory, no output formatting"}
 
 
+def tool_level(g, idx, cores):
+    """FASTQ files in, SAM file out: dart_b200_map (reader thread + GPU-side FASTQ parse, mapping and SAM text + pwrite pool) next to
+    the stock reference binary on the SAME files (tmpfs when the box has one), index load excluded on both sides.  This is the
+    number a user of the tool sees; it is bounded by file IO, not by the GPU."""
+    import re
+    from dart_b200 import synth
+    d = "/dev/shm/dart_b200_tool" if os.path.isdir("/dev/shm") else os.path.join(WORK, "tool")
+    os.makedirs(d, exist_ok=True)
+    pairs = int(os.environ.get("DART_BENCH_TOOL_PAIRS", 4_000_000))
+    r1, r2 = os.path.join(d, f"t{pairs}_1.fq"), os.path.join(d, f"t{pairs}_2.fq")
+    if not (os.path.exists(r1) and os.path.exists(r2)):
+        with open(r1, "wb") as f1, open(r2, "wb") as f2:
+            done = 0
+            while done < pairs:
+                k = min(1_000_000, pairs - done)
+                m1, m2 = make_pairs(g, k, 100 + done // 1_000_000)
+                f1.write(synth.fastq_bytes(m1, 1, first_id=done)); f2.write(synth.fastq_bytes(m2, 2, first_id=done))
+                done += k
+    tool = os.path.join(ROOT, "dart_b200", "dart_b200_map")
+    best = None
+    for _ in range(3):
+        p = subprocess.run([tool, "-i", idx, "-f", r1, "-f2", r2, "-o", os.path.join(d, "gpu.sam"), "-j", os.path.join(d, "gpu.junc")],
+                           capture_output=True, text=True, check=True)
+        sec = float(re.search(r"processed in ([0-9.]+) seconds", p.stdout).group(1))
+        best = sec if best is None else min(best, sec)
+    # the reference on a quarter of the same files (it is ~5x slower), index-load time subtracted
+    rp = min(pairs, 500_000)
+    q1, q2 = os.path.join(d, "q_1.fq"), os.path.join(d, "q_2.fq")
+    for src, dst in ((r1, q1), (r2, q2)):
+        with open(src, "rb") as f, open(dst, "wb") as o:
+            for _ in range(4 * rp):
+                o.write(f.readline())
+    e1, e2 = os.path.join(d, "one_1.fq"), os.path.join(d, "one_2.fq")
+    for src, dst in ((r1, e1), (r2, e2)):
+        with open(src, "rb") as f, open(dst, "wb") as o:
+            for _ in range(4):
+                o.write(f.readline())
+    load = min(time_reference(idx, e1, e2, 2, cores, []) for _ in range(2))
+    t_ref = max(time_reference(idx, q1, q2, 2 * rp, cores, []) - load, 1e-6)
+    out = {"gpu_reads_per_s": 2 * pairs / best, "gpu_seconds": best, "pairs": pairs,
+           "fastq_bytes": os.path.getsize(r1) + os.path.getsize(r2), "sam_bytes": os.path.getsize(os.path.join(d, "gpu.sam")),
+           "reference_reads_per_s": 2 * rp / t_ref, "reference_pairs": rp, "reference_threads": cores,
+           "what": "dart_b200_map vs dart_ref -t <cores> on the same FASTQ files, FASTQ -> SAM + junctions.tab, index load excluded, best of 3 (GPU) / one run (reference)"}
+    for f in (os.path.join(d, "gpu.sam"), q1, q2):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    return out
+
+
 def workload_config(sample_pairs=None):
     wl = ("BASELINE config[1]: synthetic 4.6 Mbp random genome (seed 1001), paired-end 2x101 bp, 1% substitutions, FR fragments ~N(300,30)"
           if WORKLOAD == "c2" else
@@ -500,6 +551,11 @@ def main():
                 line["cpu_baseline_hotpath"] = hotpath_baseline(g, idx, cores)
             except Exception as ex:
                 line["cpu_baseline_hotpath"] = {"value": None, "sample": f"failed: {ex}"}
+            if WORKLOAD == "c2" and os.environ.get("DART_BENCH_TOOL", "1") != "0":
+                try:
+                    line["fastq_to_sam"] = tool_level(g, idx, cores)
+                except Exception as ex:
+                    line["fastq_to_sam"] = {"failed": repr(ex)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -100,11 +100,12 @@ __global__ void k_pair_prune(int n_units, int paired, const int64_t *seed_off, c
 // kernel that may run it takes its configuration (5 CTAs per SM, 8 staged seeds); D alone runs 8 CTAs per SM.
 // The candidate count lives on the device (E.ctl->ncand); `slice_off` = the prefix sum that places this phase's pool slices
 // (A: seed pool, D: CIGAR pool).
-// Phase D (CIGAR pairs, score, coordinates) needs a slice of the CIGAR pool sized by phase C.  Round 1 placed the slices with a
-// prefix sum over all candidates between C and D, so every candidate was loaded and stored once more by a fourth kernel
-// (0.52 ms of a 5 ms step on config[1]).  Now the slice is claimed from a counter in the control block at a point where the
-// whole warp is converged (one atomic per warp), and a candidate whose phase C queued no alignment job runs D in the same
-// thread, right away: on config[1] that is nearly every candidate, and the fourth kernel finds almost nothing left to do.
+// Phase D (CIGAR pairs, score, coordinates) needs a slice of the CIGAR pool sized by phase C.  Round 1 placed the slices with
+// two helper kernels and a prefix sum over all candidates between C and D; now the slice is claimed from a counter in the
+// control block at a point where the whole warp is converged (one atomic per warp).
+// Measured and dropped (round 2, config[1]): running D in the same thread right behind C for the candidates that queued no
+// alignment.  The merged kernel inherits C's 96 registers / 5 CTAs per SM, and these passes are chains of dependent loads
+// whose only remedy is occupancy: phase A-C grew from 0.60 to 1.61 ms while the D pass only shrank from 0.52 to 0.06 ms.
 __device__ __forceinline__ long long warp_claim(long long *counter, int need)
 {   // all 32 lanes call this together; returns the start of this lane's `need` slots
     const int lane = threadIdx.x & 31;
@@ -124,7 +125,13 @@ __device__ __forceinline__ long long warp_claim(long long *counter, int need)
 // active, 26 % of the warp slots occupied).
 struct PhaseQueues { uint32_t *q[3]; };          // candidates waiting for phase 1 (B), 2 (C), 3 (D)
 
-template <int WHICH> struct PhaseCfg { static constexpr int STAGE = 8, MIN_CTAS = 5; };
+// Occupancy: C keeps the most state live (96 registers), and any kernel that may run it takes its configuration (5 CTAs per
+// SM, 8 staged seeds); D alone runs 6 CTAs per SM (80 registers: with the in-place alignment of tiny blocks 8 CTAs spill; measured
+// 0.68 ms at 8, 0.59 ms at 7 and 6 on config[1]).
+#ifndef PHASE3_CTAS
+#define PHASE3_CTAS 6
+#endif
+template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 3 ? 5 : 8, MIN_CTAS = WHICH == 3 ? PHASE3_CTAS : 5; };
 template <int WHICH>
 __global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E, const int64_t *__restrict__ slice_off, long long cap_cig, PhaseQueues Q)
 {
@@ -170,21 +177,18 @@ __global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E,
             }
             if (WHICH == 2) { phase_c(E, c, sv); next = 3; }
             if (WHICH == 3) want_d = true;
-            else if (next == 3) {                   // C just ran: D can follow at once unless C queued an alignment
-                bool waits = false;
-                for (int i = 0; i < c.sv_n; i++) waits |= sv[i].job >= 0;
-                want_d = !waits;
-            }
         }
-        // ---- the whole warp: claim the CIGAR slices of the candidates that run D now ----
-        __syncwarp();
-        const int need = (want_d && !c.skip) ? c.cig_cap : 0;
-        const long long off = warp_claim(&E.ctl->cig_total, need);
-        if (want_d) {
-            c.cig_off = off;
-            if (off + need > cap_cig) { atomicOr(&E.ctl->abort, CAP_CIG); c.cig_cap = 0; }     // the batch is re-run with a bigger pool
-            phase_d(E, c, sv);
-            next = 4;
+        if (WHICH == 3) {
+            // ---- the whole warp: claim the CIGAR slices ----
+            __syncwarp();
+            const int need = (want_d && !c.skip) ? c.cig_cap : 0;
+            const long long off = warp_claim(&E.ctl->cig_total, need);
+            if (want_d) {
+                c.cig_off = off;
+                if (off + need > cap_cig) { atomicOr(&E.ctl->abort, CAP_CIG); c.cig_cap = 0; }     // the batch is re-run with a bigger pool
+                phase_d(E, c, sv);
+                next = 4;
+            }
         }
         if (run) {
             if (staged) for (int i = 0; i < c.sv_n; i++) g[i] = sv[i];
