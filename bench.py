@@ -263,23 +263,29 @@ class Lanes:
         for m, sb in zip(self.mappers, self.subs):
             m.upload_reads(sb)
 
+    def results_on_device(self, on):
+        for m in self.mappers:
+            m.results_on_device(on)
+        self.on_device = on
+
     def run(self, resident, steps):
         """`steps` passes over the batch.  No barrier between steps: a context is only waited for when it is needed again."""
         K = len(self.mappers)
         parts = PARTS
         busy = [False] * K
+        how = "device" if getattr(self, "on_device", False) else False
         k = 0
         for _ in range(steps * parts):
             m = self.mappers[k]
             if busy[k]:
-                m.wait(copy=False)
+                m.wait(copy=how)
             m.submit(None if resident else self.subs[k])
             busy[k] = True
             k = (k + 1) % K
         for i in range(K):             # oldest first
             j = (k + i) % K
             if busy[j]:
-                self.mappers[j].wait(copy=False)
+                self.mappers[j].wait(copy=how)
 
     def stats(self):
         """Work and event times of one step: the last batch of every context, scaled from K batches to PARTS."""
@@ -353,15 +359,20 @@ def human_leg(args, rank, world, local, capi, barrier, allmax, peaks):
     prep_s = time.perf_counter() - t0
     steps, warm = args.steps, max(3, args.warmup)
     lanes.upload()
+    lanes.results_on_device(True)
     lanes.run(True, warm)
     ms_res = allmax(timed_region(barrier, lambda: lanes.run(True, steps)))
     st = lanes.stats()
+    lanes.results_on_device(False)
+    lanes.run(True, 2)
+    ms_res_copy = allmax(timed_region(barrier, lambda: lanes.run(True, steps)))
     lanes.run(False, 2)
     ms_e2e = allmax(timed_region(barrier, lambda: lanes.run(False, steps)))
     st_e2e = lanes.stats()
     out = {"workload": f"BASELINE config[2] at x{scale} of full size: {int(3.1e9 * scale / 1e6)} Mbp genome in 24 contigs with gene models, "
                        f"spliced pairs 2x101 bp, 1% substitutions; {pairs} pairs per GPU and step",
            "value": world * batch.n * steps / (ms_res * 1e-3), "unit": "reads/s", "ms_per_step": ms_res / steps,
+           "value_with_result_copy": world * batch.n * steps / (ms_res_copy * 1e-3),
            "e2e": {"value": world * batch.n * steps / (ms_e2e * 1e-3), "unit": "reads/s",
                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
            "n_gpus": world, "steps": steps, "warmup": warm, "prep_seconds_untimed": prep_s,
@@ -382,6 +393,40 @@ def human_leg(args, rank, world, local, capi, barrier, allmax, peaks):
                                "note": "3.1 GB Occ table + 1 GB start table: random sector gathers from HBM (L2 hit ~6 %)"}
     for m in lanes.mappers:
         m.close()
+    return out
+
+
+def host_link_probe(torch, barrier, allmax, world):
+    """What the host side of PCIe gives ALL ranks at once: every rank copies 256 MB page-locked <-> device at the same time
+    (after a barrier), CUDA-event timed, slowest rank reported.  `e2e` moves ~168 bytes per read over this link (ASCII bases in,
+    records out); at N GPUs x 0.3-0.4 G reads/s per GPU that is the shared resource of a path without any collective."""
+    n = 256 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, fn in (("h2d", lambda: d.copy_(h, non_blocking=True)), ("d2h", lambda: h.copy_(d, non_blocking=True)),
+                     ("both", None)):
+        if fn is None:
+            s2 = torch.cuda.Stream()
+            h2 = torch.empty(n, dtype=torch.uint8).pin_memory(); d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+
+            def fn():
+                d.copy_(h, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h2.copy_(d2, non_blocking=True)
+        fn(); torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            fn()
+        if name == "both":
+            torch.cuda.current_stream().wait_stream(s2)
+        e1.record(); torch.cuda.synchronize()
+        ms = allmax(e0.elapsed_time(e1))
+        out[name + "_gbs_per_gpu"] = (2 if name == "both" else 1) * 4 * n / (ms * 1e-3) / 1e9
+    out["ranks_copying_at_once"] = world
+    out["aggregate_both_gbs"] = out["both_gbs_per_gpu"] * world
     return out
 
 
@@ -432,11 +477,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    numa_bound = capi.bind_host_thread(local)       # page-locked buffers and the driving thread next to this rank's GPU
     if rank == 0:
         g, idx = prepare_genome()
     barrier()
     if rank != 0:
         g, idx = prepare_genome()
+    link = host_link_probe(torch, barrier, allmax, world)
     params = dict(pair_end=1)
     if MIS:
         params["max_mismatch"] = int(MIS)
@@ -451,12 +498,18 @@ def main():
     lanes = make_lanes(capi, idx, local, params, batch, CONTEXTS)
     M = lanes.mappers[0]
 
-    # ---- device-resident arm ----
+    # ---- device-resident arm: reads AND records stay in HBM, nothing crosses PCIe in the timed region ----
     lanes.upload()
+    lanes.results_on_device(True)
     lanes.run(True, args.warmup)
     sampler = ClockSampler(local); sampler.start()
     ms_res = allmax(timed_region(barrier, lambda: lanes.run(True, args.steps)))
     st = lanes.stats()
+    # ---- the same with the records copied to page-locked host memory every step (round 1's definition of `value`) ----
+    lanes.results_on_device(False)
+    lanes.run(True, max(1, args.warmup // 2))
+    ms_res_copy = allmax(timed_region(barrier, lambda: lanes.run(True, args.steps)))
+    st_copy = lanes.stats()
     # ---- end-to-end arm (host buffers in, host results out) ----
     lanes.run(False, max(1, args.warmup // 2))
     ms_e2e = allmax(timed_region(barrier, lambda: lanes.run(False, args.steps)))
@@ -505,8 +558,14 @@ def main():
             "data": "synthetic", "config": workload_config(), "clocks": clocks,
             "e2e": {"value": world * n_reads * args.steps / (ms_e2e * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"])},
+            "value_definition": "reads and result records resident in HBM: no PCIe traffic inside the timed region (dartgpu_set_result_location); "
+                                "value_with_result_copy = the same with the records copied to page-locked host memory every step (round 1's `value`); "
+                                "e2e = host buffers both ways",
+            "value_with_result_copy": {"value": world * n_reads * args.steps / (ms_res_copy * 1e-3), "unit": "reads/s", "ms_per_step": ms_res_copy / args.steps,
+                                       "d2h_bytes_per_step": int(st_copy["d2h_bytes"])},
             "gpu_launches": int(st["kernel_launches"]) * args.steps, "contexts_per_gpu": CONTEXTS, "batches_per_step": PARTS, "host_threads_per_gpu": 1,
             "host_sync": os.environ.get("DARTGPU_SYNC", "block (one sleeping wait per batch)"), "host_cores": os.cpu_count(),
+            "host_thread_bound_to_gpu_numa_node": bool(numa_bound), "host_link": link,
             "roofline": roof,
             "kernels_ms_per_step": {k: st[k] for k in ("ms_search", "ms_locate", "ms_sort_cluster", "ms_kmer", "ms_nw", "ms_report", "ms_d2h", "ms_host")},
             "work_per_step": {k: int(st[k]) for k in ("ext_steps", "ext_blocks", "search_sector_loads", "lf_steps", "hits", "seeds", "nw_jobs", "nw_cells", "kmer_jobs", "kmer_window_bases")},

@@ -90,7 +90,8 @@ EXPORTS = ["dartgpu_default_params", "dartgpu_create", "dartgpu_create_from_file
            "dartgpu_upload_reads", "dartgpu_seed_and_cluster_resident", "dartgpu_synchronize",
            "dartgpu_map_reads_resident", "dartgpu_index_build", "dartgpu_measure_int32_peak", "dartgpu_measure_l2_peak",
            "dartgpu_submit", "dartgpu_submit_resident", "dartgpu_wait", "dartgpu_submit_fastq", "dartgpu_wait_sam",
-           "dartgpu_fastq_cut", "dartgpu_alloc_pinned", "dartgpu_free_pinned"]
+           "dartgpu_fastq_cut", "dartgpu_alloc_pinned", "dartgpu_free_pinned", "dartgpu_set_result_location",
+           "dartgpu_bind_host_thread"]
 
 
 def load_library() -> C.CDLL:
@@ -113,6 +114,8 @@ def load_library() -> C.CDLL:
     L.dartgpu_sequence_length.restype = C.c_int64
     L.dartgpu_sequence_length.argtypes = [C.c_void_p, C.c_int]
     L.dartgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.dartgpu_set_result_location.argtypes = [C.c_void_p, C.c_int]
+    L.dartgpu_bind_host_thread.argtypes = [C.c_int]
     L.dartgpu_seed_and_cluster.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_Seeds)]
     L.dartgpu_kmer_reseed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.dartgpu_nw_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(_NwResult)]
@@ -216,6 +219,10 @@ class Mapper:
         for k, v in params.items():
             setattr(self.params, k, v)
         self._check(self.L.dartgpu_set_params(self.h, C.byref(self.params)))
+
+    def results_on_device(self, on: bool):
+        """Leave the records in HBM (device pointers in the result) instead of copying them to the host."""
+        self._check(self.L.dartgpu_set_result_location(self.h, int(bool(on))))
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self.L.dartgpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
@@ -328,6 +335,9 @@ class Mapper:
 
     @staticmethod
     def _result(out, copy):
+        if copy == "device":   # results left in HBM: counts only
+            return dict(n_reads=out.n_reads, n_reports=out.n_reports, n_cigar_bytes=out.n_cigar_bytes, n_junctions=out.n_junctions,
+                        dev_reads=out.reads, dev_reports=out.reports, dev_cigars=out.cigars, dev_junctions=out.junctions)
         if not copy:  # views into context-owned memory, valid until the next call
             return dict(reads=_view(out.reads, READ_RESULT, out.n_reads), reports=_view(out.reports, REPORT, out.n_reports),
                         n_cigar_bytes=out.n_cigar_bytes, junctions=_view(out.junctions, JUNCTION, out.n_junctions))
@@ -335,6 +345,11 @@ class Mapper:
                     reports=_view(out.reports, REPORT, out.n_reports).copy(),
                     cigars=_view(out.cigars, np.uint8, out.n_cigar_bytes).tobytes(),
                     junctions=_view(out.junctions, JUNCTION, out.n_junctions).copy())
+
+
+def bind_host_thread(device: int) -> bool:
+    """Pin this thread to the CPUs of the GPU's NUMA node (before creating Mappers: their pinned buffers follow)."""
+    return load_library().dartgpu_bind_host_thread(int(device)) == 0
 
 
 def index_build(genome, prefix: str, device: int = 0, max_suffixes_per_pass: int = 0) -> None:

@@ -2,6 +2,7 @@
 // There is deliberately no CPU implementation behind any entry point: without a CUDA device
 // dartgpu_create* fails with DARTGPU_ERR_NO_DEVICE and nothing else can be called.
 #include <omp.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -842,6 +843,39 @@ int64_t dartgpu_genome_size(const dartgpu_ctx *c) { return c ? c->G : 0; }
 int dartgpu_num_sequences(const dartgpu_ctx *c) { return c ? (int)c->shared->names.size() : 0; }
 const char *dartgpu_sequence_name(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->shared->names.size()) ? c->shared->names[i].c_str() : ""; }
 int64_t dartgpu_sequence_length(const dartgpu_ctx *c, int i) { return (c && i >= 0 && i < (int)c->shared->chr_len.size()) ? c->shared->chr_len[i] : 0; }
+int dartgpu_set_result_location(dartgpu_ctx *c, int on_device)
+{
+    if (!c) return DARTGPU_ERR_ARG;
+    if (c->in_flight) return fail(c, DARTGPU_ERR_ARG, "a submitted batch is still in flight on this context: dartgpu_wait first");
+    c->results_on_device = on_device != 0;
+    return DARTGPU_OK;
+}
+
+// Pins the calling host thread to the CPUs next to `device` (its PCIe root: /sys/bus/pci/devices/<bus id>/local_cpulist), so
+// that the page-locked buffers the thread allocates afterwards and its copies stay on the GPU's own NUMA node.
+int dartgpu_bind_host_thread(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return DARTGPU_ERR_ARG; }
+    for (char *p = bus; *p; p++) if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) return DARTGPU_ERR_ARG;
+    char line[4096] = {0};
+    const bool ok = fgets(line, sizeof line, fp) != nullptr;
+    fclose(fp);
+    if (!ok) return DARTGPU_ERR_ARG;
+    cpu_set_t set; CPU_ZERO(&set);
+    int n_set = 0;
+    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int i = a; i <= b && i < CPU_SETSIZE; i++) { CPU_SET(i, &set); n_set++; } }
+        else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) { CPU_SET(a, &set); n_set++; }
+    }
+    if (!n_set) return DARTGPU_ERR_ARG;
+    return sched_setaffinity(0, sizeof set, &set) == 0 ? DARTGPU_OK : DARTGPU_ERR_ARG;
+}
+
 int dartgpu_set_stream(dartgpu_ctx *c, void *s)
 {
     if (!c) return DARTGPU_ERR_ARG;

@@ -247,6 +247,7 @@ int main(int argc, char **argv)
         std::vector<std::map<std::pair<int64_t, int64_t>, std::pair<int, int>>> sj(nd);
         std::vector<int64_t> w_reads(nd, 0), w_unm(nd, 0), w_uq(nd, 0), w_prd(nd, 0);
         auto worker = [&](int d) {
+            dartgpu_bind_host_thread(devices[d]);       // stay on the GPU's NUMA node (best effort)
             std::deque<std::pair<dartgpu_ctx *, Block *>> flying;
             auto fail_all = [&](const char *what, dartgpu_ctx *c, int rc) {
                 fprintf(stderr, "%s failed (%d): %s\n", what, rc, dartgpu_last_error(c));

@@ -472,6 +472,7 @@ void enqueue_pipeline(dartgpu_ctx *c)
     DG_CUDA(cudaEventRecord(c->ev[13], st));
     compute_turn_end(c);                     // the next batch's kernels (any context of this device) may start: the copies below run under them
 
+    if (c->results_on_device) { D->sent_rep = D->sent_text = D->sent_junc = 0; DG_CUDA(cudaEventRecord(c->ev[14], st)); return; }
     // ---- only the final records cross PCIe.  Their sizes are known on the device only: the copies cover what the previous
     // batch of this context needed plus a margin (a guess the first time); finish_pipeline tops up.
     D->sent_rep = predict(D->last_rep, cap_r, (int64_t)n + n / 2 + 1024);
@@ -494,6 +495,13 @@ void finish_pipeline(dartgpu_ctx *c, dartgpu_map_result *out)
     const int n = c->n_reads;
     const BatchCtl &H = c->h_ctl.p[0];
     const int64_t nrep = H.nrep, text_total = H.text_total, junc_total = H.junc_total;
+    if (c->results_on_device) {          // dartgpu_set_result_location(ctx, 1): the records stay in HBM, the pointers are device pointers
+        out->reads = D->rr.p; out->n_reads = n;
+        out->reports = D->rep.p; out->n_reports = nrep;
+        out->cigars = D->text.p; out->n_cigar_bytes = text_total;
+        out->junctions = D->junc.p; out->n_junctions = junc_total;
+        return;
+    }
     bool more = false;
     auto top_up = [&](auto &hbuf, const auto &dbuf, int64_t sent, int64_t total, size_t elem) {
         if (total <= sent) return;

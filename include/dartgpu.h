@@ -94,6 +94,13 @@ int64_t dartgpu_genome_size(const dartgpu_ctx *ctx);
 int  dartgpu_num_sequences(const dartgpu_ctx *ctx);
 const char *dartgpu_sequence_name(const dartgpu_ctx *ctx, int i);
 int64_t dartgpu_sequence_length(const dartgpu_ctx *ctx, int i);
+/* Where dartgpu_wait / dartgpu_map_reads leave the records: 0 (default) = the context's page-locked host buffers;
+ * 1 = device memory: the pointers of dartgpu_map_result are then DEVICE pointers and nothing crosses PCIe (for callers
+ * that consume the records on the GPU, and for device-resident timing: bench.py `value`). */
+int  dartgpu_set_result_location(dartgpu_ctx *ctx, int on_device);
+/* Pins the calling host thread to the CPUs of `device`'s NUMA node (call it before creating the thread's contexts, so that
+ * their page-locked buffers are allocated next to the GPU). */
+int  dartgpu_bind_host_thread(int device);
 /* Work on `stream` (a cudaStream_t) instead of the context's own stream, e.g. the caller's current stream. */
 int  dartgpu_set_stream(dartgpu_ctx *ctx, void *cuda_stream);
 

@@ -69,3 +69,31 @@ def test_in_flight_batches_equal_synchronous_calls():
     assert st["kernel_launches"] > 20 and st["ms_search"] > 0
     for m in ms:
         m.close()
+
+
+def test_results_can_stay_on_the_device():
+    """dartgpu_set_result_location(ctx, 1): the records stay in HBM (what bench.py's `value` times); copied back by hand they
+    are the records the default mode delivers."""
+    from cuda import cudart
+    w = workload("c2")
+    batch = _batch(w)
+    m = capi.Mapper(w["idx"], device=0, pair_end=1)
+    want = m.map_reads(batch)
+    m.results_on_device(True)
+    m.submit(batch)
+    got = m.wait(copy="device")
+    assert (got["n_reads"], got["n_reports"], got["n_cigar_bytes"], got["n_junctions"]) == \
+           (len(want["reads"]), len(want["reports"]), len(want["cigars"]), len(want["junctions"]))
+
+    def fetch(ptr, dtype, n):
+        a = np.empty(n, dtype=dtype)
+        if n:
+            err, = cudart.cudaMemcpy(a.ctypes.data, ptr, a.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+            assert err == cudart.cudaError_t.cudaSuccess
+        return a
+    assert fetch(got["dev_reads"], capi.READ_RESULT, got["n_reads"]).tobytes() == want["reads"].tobytes()
+    assert fetch(got["dev_reports"], capi.REPORT, got["n_reports"]).tobytes() == want["reports"].tobytes()
+    assert fetch(got["dev_cigars"], np.uint8, got["n_cigar_bytes"]).tobytes() == want["cigars"]
+    m.results_on_device(False)
+    _same(want, m.map_reads(batch))
+    m.close()
