@@ -498,7 +498,16 @@ static const uint8_t *upload_job_bases(dartgpu_ctx *c, const char *bases, int64_
 // ---------------------------------------------------------------------------------------------------
 // index hand-over
 // ---------------------------------------------------------------------------------------------------
-SharedIndex::~SharedIndex() { cudaSetDevice(device); }   // the DevBuf members free on the right device
+// the DevBuf members must be freed on their device; the caller's current device is put back afterwards (here the members are
+// still alive, so: free them by hand, then restore)
+SharedIndex::~SharedIndex()
+{
+    int cur = -1;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    d_occ32.release(); d_sa.release(); d_ktab.release(); d_ref2.release(); d_ends.release(); d_chr_names.release(); d_chr_name_off.release();
+    if (cur >= 0) cudaSetDevice(cur);
+}
 
 // identity of an index for sharing (device and SA density not included): header fields + a hash of samples of the tables
 static std::string index_key(int device, const dartgpu_index_view *v, int sa_shift, bool force64)
@@ -553,11 +562,24 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
     const std::string ident = index_key(device, v, sa_shift, force64);
     const bool shift_pinned = getenv("DARTGPU_SA_SAMPLE") != nullptr;
     std::shared_ptr<SharedIndex> peer;                       // the same index, resident on another GPU of this process
-    for (auto &kv : g_indexes) {
-        auto sp = kv.second.lock();
-        if (!sp || sp->ident != ident || (shift_pinned && sp->ix.sa_shift != sa_shift)) continue;
+    for (auto it = g_indexes.begin(); it != g_indexes.end();) {
+        auto sp = it->second.lock();
+        if (!sp) { it = g_indexes.erase(it); continue; }     // its last context is gone
+        ++it;
+        if (sp->ident != ident || (shift_pinned && sp->ix.sa_shift != sa_shift)) continue;
         if (sp->device == device) return sp;                 // same device: share it
         if (!peer) peer = sp;
+    }
+    if (peer) {
+        // the peer's layout (its SA density and start table) must fit THIS device's free memory, else load from the host with
+        // a density chosen for this device
+        size_t free_b = 0, total_b = 0;
+        DG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = occ_bytes + ref_words * 4 + ((v->seq_len >> peer->ix.sa_shift) + 2) * sa_width +
+                            (peer->ix.ktab ? ((size_t)1 << (2 * peer->ix.ktab_k)) * sizeof(KmerStart) : 0) + (256u << 20);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, device, peer->device);
+        if (need > free_b || !can) { cudaGetLastError(); peer.reset(); }
     }
     if (peer) sa_shift = peer->ix.sa_shift;
     const std::string key = std::to_string(device) + ":" + ident + ":" + std::to_string(sa_shift);
@@ -595,9 +617,7 @@ static std::shared_ptr<SharedIndex> load_shared_index(int device, const dartgpu_
     if (peer) {
         // Replicate GPU -> GPU (NVLink / NVSwitch: cudaMemcpyPeer) instead of a second host->device upload, re-layout and
         // LF pass: for the 3.1 Gbp index that is ~31 GB over the switch instead of 5.4 GB over PCIe + 0.5 s of kernels.
-        int can = 0;
-        cudaDeviceCanAccessPeer(&can, device, peer->device);
-        if (can) { cudaError_t pe = cudaDeviceEnablePeerAccess(peer->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
+        { cudaError_t pe = cudaDeviceEnablePeerAccess(peer->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
         const size_t sa_bytes = ((v->seq_len >> sa_shift) + 2) * sa_width;
         const size_t kt_entries = peer->ix.ktab ? ((size_t)1 << (2 * peer->ix.ktab_k)) : 0;
         S->d_occ32.reserve(occ_bytes); S->d_sa.reserve(sa_bytes); S->d_ref2.reserve(ref_words); S->d_ends.reserve(S->ends.size());
@@ -814,6 +834,9 @@ int dartgpu_index_build(int device, const uint8_t *pac, int64_t l_pac, const cha
 void dartgpu_destroy(dartgpu_ctx *c)
 {
     if (!c) return;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{cur};      // the caller's current device stays what it was
     cudaSetDevice(c->device);
     if (c->in_flight) cudaStreamSynchronize(c->stream);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
