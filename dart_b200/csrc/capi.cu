@@ -253,6 +253,8 @@ void enqueue_seeding(dartgpu_ctx *c)
     a.cap_rec = c->cap_rec; a.max_dup = c->prm.max_dup; a.max_gaps = c->prm.max_gaps; a.max_intron = c->prm.max_intron;
     a.recs = c->d_recs.p; a.nrec = c->d_nrec.p; a.nhits = c->d_nhits.p; a.seed_off = c->d_seed_off.p;
     a.ncand = c->d_ncand.p; a.big_list = c->d_big_list.p; a.big_count = &c->d_ctl.p->big_count; a.mid_list = c->d_mid_list.p; a.mid_count = &c->d_ctl.p->mid_count;
+    static const bool always_count = [] { const char *e = getenv("DARTGPU_STATS"); return e && atoi(e) != 0; }();
+    a.count_work = (!c->whole_path_enqueue || always_count) ? 1 : 0;
     a.ctl = c->d_ctl.p; a.stats = &c->d_ctl.p->stats; a.packed = c->d_packed.p; a.steal = &c->d_ctl.p->steal;
     a.keys = c->d_keys.p; a.meta = c->d_meta.p;
     a.cand_begin = c->d_cand_begin.p; a.cand_count = c->d_cand_count.p; a.cand_score = c->d_cand_score.p;
@@ -337,6 +339,7 @@ static void run_seeding_sync(dartgpu_ctx *c, bool fetch)
     c->total_seeds = 0;
     if (n == 0) { c->o_cand_off.assign(1, 0); c->h_seed_off.reserve(1); c->h_seed_off.p[0] = 0; return; }
     caps_for_batch(c);
+    c->whole_path_enqueue = false;               // the stage entry points keep the work counters
     for (int attempt = 0;; attempt++) {
         ctl_begin(c);
         enqueue_seeding(c);
@@ -1003,8 +1006,10 @@ static void enqueue_whole_path(dartgpu_ctx *c)
 {
     compute_turn_begin(c);
     ctl_begin(c);
+    c->whole_path_enqueue = true;
     if (c->from_fastq) k_ctl_ingest<<<1, 1, 0, c->stream>>>(c->d_ctl.p, c->max_rlen);
     enqueue_seeding(c);
+    c->whole_path_enqueue = false;
     enqueue_pipeline(c);
     ctl_fetch(c);
     DG_CUDA(cudaEventRecord(c->done, c->stream));

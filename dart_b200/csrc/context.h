@@ -97,6 +97,7 @@ struct dartgpu_ctx {
     int64_t total_seeds = 0;
     // ---- the batch in flight (dartgpu_submit .. dartgpu_wait) ----
     bool in_flight = false, whole_path = false, timed_upload = false;
+    bool whole_path_enqueue = false;              // set around enqueue_seeding by the whole-path calls: k_search runs without work counters
     bool results_on_device = false;               // dartgpu_set_result_location
     bool from_fastq = false, emit_sam = false;    // the batch came as FASTQ text / leaves as SAM text (dartgpu_submit_fastq)
     dartgpu::FastqDev fq;

@@ -193,6 +193,7 @@ struct SeedLaunch {
     uint64_t *big_scratch; size_t big_scratch_per_cta;          // global sort scratch for reads that exceed smem
     DevStats *stats;
     BatchCtl *ctl;                                              // ctl->total_seeds bounds the per-hit kernels
+    int count_work;                                             // k_search keeps the work counters (stage entry points, DARTGPU_STATS=1)
 };
 void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st);
 void launch_scan_hits(const SeedLaunch &a, void *tmp, size_t tmp_bytes, cudaStream_t st);

@@ -84,7 +84,11 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 // still has a queue (the grid is exactly one wave).  Results are indexed by read, so the order does not matter.
 // The work counters keep the reference's definition (a step touches one 64-byte BWA block or two, bwt_search.cpp:88-93).
 // ---------------------------------------------------------------------------------------------------
-template <typename IdxT>
+// COUNT: keep the reference's work counters (steps, 64-byte blocks, sectors requested).  They cost ~5 of the ~45 instructions
+// of a step on a kernel that is bound by instruction issue, so the whole-path calls run without them; the stage entry points
+// (and DARTGPU_STATS=1) run with them — that is where the tests compare them with the oracle's and where bench.py reads the
+// algorithmic bytes of the roofline.
+template <typename IdxT, bool COUNT>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_search(DevIndex ix, SeedLaunch a, int per_cta)
 {
@@ -115,17 +119,30 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
     const int TURN_BATCH = a.turn_batch, END_BATCH = a.end_batch;
     bool own = true, have_read = false;
     int st = ST_NEED;
-    int r = 0, rl = 0, start = 0, p = 0, cw = -1;
+    int r = 0, rl = 0, start = 0, p = 0, cw = -2;
     int64_t wbase = 0;
-    uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0, kidx = 0;
+    uint32_t nr = 0, nh = 0, x2 = 0, wcode = 0, wamb = 0, ncode = 0, namb = 0, kidx = 0;
     IdxT x1 = 0;
     uint32_t st_steps = 0, st_splits = 0, st_loads = 0;
 
+    // The packed view of the read under the cursor: word cw (16 bases) and, prefetched, word cw + 1.  Round-2 finding: the
+    // step path loaded the next word when it crossed a 16-base boundary, and the ambiguity bit of that word gates the rank
+    // load — two dependent L2 round trips in that iteration.  Now the word behind the cursor is requested 16 steps before it is
+    // needed.  Measured on config[1]: 1.72 -> 1.71 ms per 2 M reads — no difference: on the L2-resident index the kernel is
+    // bound by instruction issue (68-78 % issue-active at 19.5 of 32 lanes), not by latency.  Kept: it is the cheaper code.
+    auto fetch = [&](int w) {
+        if (w == cw) return;
+        if (w == cw + 1) { wcode = ncode; wamb = namb; }
+        else { const uint2 x = __ldg(a.packed + wbase + w); wcode = x.x; wamb = x.y; }
+        const uint2 y = __ldg(a.packed + wbase + w + 1);          // one entry past the read is padding or the next read: never used
+        ncode = y.x; namb = y.y;
+        cw = w;
+    };
     // next search start of the current read: skip ambiguous bases, then either a table lookup (JUMP) or the reference's
     // single-base start (STEP); NEED when the read has no start left (IdentifySeedPairs' `pos < rlen - 13`)
     auto advance = [&]() {
         while (start < rl - 13) {              // a search cannot start on an ambiguous base
-            if ((start >> 4) != cw) { cw = start >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+            fetch(start >> 4);
             if (!((wamb >> (start & 15)) & 1u)) break;
             start++;
         }
@@ -133,10 +150,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
         if (K > 0 && start + K <= rl) {
             const int sh = start & 15;
             uint32_t bits = wcode >> (2 * sh), ambs = wamb >> sh;
-            if (sh + K > 16) {
-                const uint2 w2 = __ldg(a.packed + wbase + cw + 1);
-                bits |= sh ? w2.x << (32 - 2 * sh) : 0u; ambs |= w2.y << (16 - sh);
-            }
+            if (sh + K > 16) { bits |= sh ? ncode << (32 - 2 * sh) : 0u; ambs |= namb << (16 - sh); }
             if ((ambs & kmask1) == 0) { kidx = bits & kmask2; st = ST_JUMP; return; }
         }
         const int c0 = (wcode >> ((start & 15) * 2)) & 3;
@@ -171,7 +185,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
             else {
                 rl = a.rlen[r];
                 wbase = a.dev_off[r] >> 4;
-                start = 0; nr = 0; nh = 0; have_read = true; cw = -1;
+                start = 0; nr = 0; nh = 0; have_read = true; cw = -2;
                 advance();
             }
         }
@@ -184,7 +198,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
             if (stepping) {
                 end = p >= rl;
                 if (!end) {
-                    if ((p >> 4) != cw) { cw = p >> 4; const uint2 w = __ldg(a.packed + wbase + cw); wcode = w.x; wamb = w.y; }
+                    fetch(p >> 4);
                     end = (wamb >> (p & 15)) & 1u;
                 }
                 if (!end) {
@@ -200,10 +214,10 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                 const OccBlock B0 = load_block(addr0, 0);
                 OccBlock B1 = B0;
                 if (two) B1 = load_block(addr1, 0);
-                st_loads += two ? 2u : 1u;                                // 32-byte sectors really requested (L2 roofline)
+                if (COUNT) st_loads += two ? 2u : 1u;                     // 32-byte sectors really requested (L2 roofline)
                 if (stepping) {
                     const uint32_t ok = block_rank(B0, (uint32_t)kk & 63u, c), ol = block_rank(B1, (uint32_t)ll & 63u, c);
-                    st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0);
+                    if (COUNT) { st_steps++; st_splits += (uint32_t)(((kk ^ ll) >> 7) != 0); }
                     const uint32_t n2 = ol - ok;
                     if (n2 == 0) end = true;
                     else { x1 = (IdxT)s_L2[c] + 1 + ok; x2 = n2; p++; }
@@ -215,7 +229,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
                     const uint32_t e_sp = hi ? (uint32_t)(B0.hi >> 32) : B0.cnt[3];
                     if (e_x2 != 0) {
                         x1 = (IdxT)e_x1; x2 = e_x2; p = start + K;
-                        st_steps += K - 1; st_splits += e_sp;
+                        if (COUNT) { st_steps += K - 1; st_splits += e_sp; }
                     } else {                        // the K-mer does not occur: start from the single base as the reference does
                         const int c0 = (int)(kidx & 3u);
                         x1 = (IdxT)s_L2[3 - c0] + 1; x2 = (uint32_t)(s_L2[c0 + 1] - s_L2[c0]);
@@ -228,6 +242,7 @@ k_search(DevIndex ix, SeedLaunch a, int per_cta)
         }
     }
     if (have_read) { a.nrec[r] = nr; a.nhits[r] = nh; }
+    if (!COUNT) return;
     __syncwarp();
     const unsigned long long ws = warp_sum(st_steps), wp = warp_sum(st_splits), wl = warp_sum(st_loads);
     if ((threadIdx.x & 31) == 0 && ws) {
@@ -252,8 +267,8 @@ void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
     SearchCfg &cfg = g_search_cfg[dev >= 0 && dev < 64 ? dev : 0];
     int occ32 = cfg.occ32.load(std::memory_order_acquire), occ64 = cfg.occ64.load(std::memory_order_acquire);
     if (!occ32 || !occ64) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k_search<uint32_t>, SEARCH_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_search<uint64_t>, SEARCH_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k_search<uint32_t, true>, SEARCH_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_search<uint64_t, true>, SEARCH_THREADS, 0);
         occ32 = std::max(1, occ32); occ64 = std::max(1, occ64);
         cfg.occ32.store(occ32, std::memory_order_release); cfg.occ64.store(occ64, std::memory_order_release);
     }
@@ -269,8 +284,13 @@ void launch_search(const DevIndex &ix, SeedLaunch a, cudaStream_t st)
     a.turn_batch = turn_batch;
     static const int end_batch = getenv("DARTGPU_END_BATCH") ? atoi(getenv("DARTGPU_END_BATCH")) : 4;
     a.end_batch = end_batch;
-    if (narrow) k_search<uint32_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
-    else k_search<uint64_t><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
+    if (a.count_work) {
+        if (narrow) k_search<uint32_t, true><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
+        else k_search<uint64_t, true><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
+    } else {
+        if (narrow) k_search<uint32_t, false><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
+        else k_search<uint64_t, false><<<grid, SEARCH_THREADS, 0, st>>>(ix, a, per_cta);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

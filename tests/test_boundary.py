@@ -111,3 +111,23 @@ def test_index_wider_than_the_seed_key_is_rejected():
         v.L2[i] = i * ((v.seq_len) // 4)
     rc = L.dartgpu_create(C.byref(h), 0, C.byref(v), None)
     assert b"33-bit" not in L.dartgpu_last_error(None)
+
+
+def test_fastq_cut_finds_record_boundaries():
+    """dartgpu_fastq_cut (host helper of the streaming tool, no GPU involved): bytes spanned by at most max_records complete
+    4-line records; a trailing partial record and a last line without newline are left for the next block."""
+    L = capi.load_library()
+    L.dartgpu_fastq_cut.restype = C.c_int64
+    L.dartgpu_fastq_cut.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32)]
+    rec = lambda i, n: b"@r%d extra\n%s\n+\n%s\n" % (i, b"ACGT" * n, b"IIII" * n)   # noqa: E731
+    recs = [rec(i, 5 + 7 * (i % 11)) for i in range(3000)]           # ~200 KB: several 64 KB counting pieces
+    text = b"".join(recs)
+    k = C.c_int32(0)
+    assert L.dartgpu_fastq_cut(text, len(text), 0, C.byref(k)) == len(text) and k.value == 3000
+    for want in (1, 2, 999, 2999, 3000, 5000):
+        used = L.dartgpu_fastq_cut(text, len(text), want, C.byref(k))
+        assert k.value == min(want, 3000) and used == len(b"".join(recs[:k.value]))
+    partial = text + b"@tail\nACGT\n+\nII"                              # no newline behind the last quality line
+    assert L.dartgpu_fastq_cut(partial, len(partial), 0, C.byref(k)) == len(text) and k.value == 3000
+    assert L.dartgpu_fastq_cut(b"@x\nAC", 5, 0, C.byref(k)) == 0 and k.value == 0
+    assert L.dartgpu_fastq_cut(b"", 0, 0, C.byref(k)) == 0 and k.value == 0
