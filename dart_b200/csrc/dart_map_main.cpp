@@ -11,7 +11,7 @@
 //
 //   dart_b200_map -i <index prefix> -f r1.fq [-f2 r2.fq] -o out.sam [-j junctions.tab] [-mis N] [-max_dup N]
 //                 [-m] [-p] [-unique] [-all_sj] [-max_intron N] [-min_intron N] [-t host threads]
-//                 [-batch reads per GPU call] [-devices 0,1,..] [-inflight contexts per GPU] [-stats] [-hostpath]
+//                 [-batch reads per GPU call] [-devices 0,1,..] [-inflight contexts per GPU] [-writers threads] [-stats] [-hostpath]
 #include <fcntl.h>
 #include <unistd.h>
 
@@ -72,7 +72,7 @@ int main(int argc, char **argv)
     const char *index = nullptr, *f1 = nullptr, *f2 = nullptr, *out_fn = "output.sam", *sj_fn = "junctions.tab";
     bool interleaved = false, want_stats = false, hostpath = false;
     int64_t batch = 1 << 19;
-    int inflight = 4;
+    int inflight = 4, writers = 0;
     std::vector<int> devices{0};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -93,6 +93,7 @@ int main(int argc, char **argv)
         else if (a == "-t") P.host_threads = atoi(next());
         else if (a == "-batch") batch = atoll(next());
         else if (a == "-inflight") inflight = std::max(1, atoi(next()));
+        else if (a == "-writers") writers = std::max(1, atoi(next()));
         else if (a == "-stats") want_stats = true;
         else if (a == "-hostpath") hostpath = true;
         else if (a == "-silent") {}
@@ -305,7 +306,7 @@ int main(int argc, char **argv)
             }
         };
         std::vector<std::thread> th, wr;
-        const int n_writers = std::max(2, std::min(8, nd * 2));
+        const int n_writers = writers > 0 ? writers : std::max(4, std::min(16, nd * 3));
         for (int i = 0; i < n_writers; i++) wr.emplace_back(writer);
         for (int d = 0; d < nd; d++) th.emplace_back(worker, d);
         for (auto &t : th) t.join();
