@@ -193,9 +193,15 @@ def tool_level(g, idx, cores):
     number a user of the tool sees; it is bounded by file IO, not by the GPU."""
     import re
     from dart_b200 import synth
-    d = "/dev/shm/dart_b200_tool" if os.path.isdir("/dev/shm") else os.path.join(WORK, "tool")
-    os.makedirs(d, exist_ok=True)
+    import shutil
     pairs = int(os.environ.get("DART_BENCH_TOOL_PAIRS", 4_000_000))
+    need = pairs * 1200                       # FASTQ + SAM + the reference's sample, with room to spare
+    d = os.path.join(WORK, "tool")
+    if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * need:
+        d = "/dev/shm/dart_b200_tool"         # tmpfs: the number then measures the tool, not the disk
+    os.makedirs(d, exist_ok=True)
+    if shutil.disk_usage(d).free < need:
+        return {"skipped": f"not enough free space under {d} for {pairs} pairs"}
     r1, r2 = os.path.join(d, f"t{pairs}_1.fq"), os.path.join(d, f"t{pairs}_2.fq")
     if not (os.path.exists(r1) and os.path.exists(r2)):
         with open(r1, "wb") as f1, open(r2, "wb") as f2:
@@ -230,7 +236,7 @@ def tool_level(g, idx, cores):
            "fastq_bytes": os.path.getsize(r1) + os.path.getsize(r2), "sam_bytes": os.path.getsize(os.path.join(d, "gpu.sam")),
            "reference_reads_per_s": 2 * rp / t_ref, "reference_pairs": rp, "reference_threads": cores,
            "what": "dart_b200_map vs dart_ref -t <cores> on the same FASTQ files, FASTQ -> SAM + junctions.tab, index load excluded, best of 3 (GPU) / one run (reference)"}
-    for f in (os.path.join(d, "gpu.sam"), q1, q2):
+    for f in (os.path.join(d, "gpu.sam"), q1, q2, r1, r2):      # leave nothing behind (tmpfs is memory)
         try:
             os.remove(f)
         except OSError:
