@@ -214,77 +214,75 @@ __global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E,
 }
 
 // ---- final pass ----
+// One thread per read (pair): best / second best, mate rescue, flags, MAPQ, then — at a point where the warp is converged —
+// the read's slice of the CIGAR-text pool and of the junction-record pool is claimed from the control block (one atomic per
+// warp and pool) and filled at once.  Round 1 / early round 2 measured the text here, ran two prefix sums over the reads and
+// wrote text and junction records in a second kernel that re-read every read, report and candidate record (0.28 ms of a
+// 4.8 ms config[1] step).  The order of the slices inside the two pools is whatever order the warps arrive in; every report
+// carries its own cigar_off and every junction record its read, and no consumer depends on the order.
 __global__ void k_read_final(Env E, int n_units, int paired, const int64_t *cand_off, const int64_t *rep_off, dartgpu_read_result *rr,
-                             dartgpu_report *rep, uint32_t *text_len, uint32_t *njunc, int n_reads)
+                             dartgpu_report *rep, char *text, dartgpu_junction *junc, long long cap_text, long long cap_junc)
 {
     if (E.ctl->abort) return;
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u - lane < n_units; u += gridDim.x * blockDim.x) {
+        const bool run = u < n_units;
         const int nr = paired ? 2 : 1;
         ReadOut ro[2];
-        for (int m = 0; m < nr; m++) {
-            int r = paired ? 2 * u + m : u;
-            read_best(E.cs + cand_off[r], (int)(cand_off[r + 1] - cand_off[r]), rep + rep_off[r], ro[m]);
-        }
-        if (!paired) finish_single(ro[0], rep + rep_off[u], E.cs + cand_off[u], (int)(cand_off[u + 1] - cand_off[u]));
-        else {
-            int a = 2 * u, b = a + 1;
-            finish_pair(ro[0], rep + rep_off[a], E.cs + cand_off[a], (int)(cand_off[a + 1] - cand_off[a]),
-                        ro[1], rep + rep_off[b], E.cs + cand_off[b], (int)(cand_off[b + 1] - cand_off[b]), E.P.multi_hit != 0);
-        }
-        for (int m = 0; m < nr; m++) {
-            int r = paired ? 2 * u + m : u;
-            dartgpu_read_result o;
-            o.mapq = (uint8_t)ro[m].mapq; o.score = (int16_t)ro[m].score; o.sub_score = (int16_t)ro[m].sub_score; o.mis_num = (int16_t)ro[m].mis_num;
-            o.n_reports = ro[m].n_reports; o.best = ro[m].best; o.report_off = rep_off[r]; o.reserved = 0;
-            rr[r] = o;
-            const int nc = (int)(cand_off[r + 1] - cand_off[r]);
-            uint32_t text = 0;                     // CIGAR text of the read's reports, laid out report after report
-            for (int k = 0; k < ro[m].n_reports; k++) {
-                int tl = 0;
-                if (k < nc) {
-                    const CandState &c = E.cs[cand_off[r] + k];
-                    if (c.cig_n < 0) atomicOr(&E.ctl->err, ERR_CIGAR_POOL);
-                    if (c.live && !c.skip && c.AlnScore > 0) tl = c.text_len;
+        int text_need = 0, junc_need = 0;
+        if (run) {
+            for (int m = 0; m < nr; m++) {
+                int r = paired ? 2 * u + m : u;
+                read_best(E.cs + cand_off[r], (int)(cand_off[r + 1] - cand_off[r]), rep + rep_off[r], ro[m]);
+            }
+            if (!paired) finish_single(ro[0], rep + rep_off[u], E.cs + cand_off[u], (int)(cand_off[u + 1] - cand_off[u]));
+            else {
+                int a = 2 * u, b = a + 1;
+                finish_pair(ro[0], rep + rep_off[a], E.cs + cand_off[a], (int)(cand_off[a + 1] - cand_off[a]),
+                            ro[1], rep + rep_off[b], E.cs + cand_off[b], (int)(cand_off[b + 1] - cand_off[b]), E.P.multi_hit != 0);
+            }
+            for (int m = 0; m < nr; m++) {
+                int r = paired ? 2 * u + m : u;
+                dartgpu_read_result o;
+                o.mapq = (uint8_t)ro[m].mapq; o.score = (int16_t)ro[m].score; o.sub_score = (int16_t)ro[m].sub_score; o.mis_num = (int16_t)ro[m].mis_num;
+                o.n_reports = ro[m].n_reports; o.best = ro[m].best; o.report_off = rep_off[r]; o.reserved = 0;
+                rr[r] = o;
+                const int nc = (int)(cand_off[r + 1] - cand_off[r]);
+                for (int k = 0; k < ro[m].n_reports; k++) {
+                    int tl = 0;
+                    if (k < nc) {
+                        const CandState &c = E.cs[cand_off[r] + k];
+                        if (c.cig_n < 0) atomicOr(&E.ctl->err, ERR_CIGAR_POOL);
+                        if (c.live && !c.skip && c.AlnScore > 0) tl = c.text_len;
+                    }
+                    rep[rep_off[r] + k].cigar_len = (int16_t)tl;
+                    text_need += tl;
                 }
-                rep[rep_off[r] + k].cigar_len = (int16_t)tl;
-                text += (uint32_t)tl;
+                junc_need += emit_junctions(E, ro[m], E.cs + cand_off[r], nc, r, nullptr);
             }
-            text_len[r] = text;
-            njunc[r] = (uint32_t)emit_junctions(E, ro[m], E.cs + cand_off[r], nc, r, nullptr);
         }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { text_len[n_reads] = 0; njunc[n_reads] = 0; }
-}
-
-__global__ void k_ctl_records(BatchCtl *ctl, const int64_t *text_off, const int64_t *junc_off, int n_reads, long long cap_text, long long cap_junc)
-{
-    if (ctl->abort) return;
-    const long long t = text_off[n_reads], j = junc_off[n_reads];
-    ctl->text_total = t; ctl->junc_total = j;
-    if (t > cap_text) atomicOr(&ctl->abort, CAP_TEXT);
-    if (j > cap_junc) atomicOr(&ctl->abort, CAP_JUNC);
-}
-
-__global__ void k_write_records(Env E, int n_reads, const int64_t *cand_off, const dartgpu_read_result *rr, dartgpu_report *rep,
-                                const int64_t *text_off, char *text, const int64_t *junc_off, dartgpu_junction *junc)
-{
-    if (E.ctl->abort) return;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
-        const dartgpu_read_result o = rr[r];
-        const int nc = (int)(cand_off[r + 1] - cand_off[r]);
-        int64_t at = text_off[r];
-        for (int k = 0; k < o.n_reports; k++) {
-            dartgpu_report &p = rep[o.report_off + k];
-            p.cigar_off = (int32_t)at;
-            if (p.cigar_len > 0 && k < nc) {
-                const CandState &c = E.cs[cand_off[r] + k];
-                write_cigar_text(E.cig + c.cig_off, c.cig_n, text + at);
+        // ---- the whole warp: claim the slices ----
+        __syncwarp();
+        const long long t0 = warp_claim(&E.ctl->text_total, text_need);
+        const long long j0 = warp_claim(&E.ctl->junc_total, junc_need);
+        if (!run) continue;
+        const bool text_ok = t0 + text_need <= cap_text, junc_ok = j0 + junc_need <= cap_junc;
+        if (!text_ok) atomicOr(&E.ctl->abort, CAP_TEXT);        // the batch is re-run with bigger pools
+        if (!junc_ok) atomicOr(&E.ctl->abort, CAP_JUNC);
+        long long at = t0, jat = j0;
+        for (int m = 0; m < nr; m++) {
+            int r = paired ? 2 * u + m : u;
+            const int nc = (int)(cand_off[r + 1] - cand_off[r]);
+            for (int k = 0; k < ro[m].n_reports; k++) {
+                dartgpu_report &p = rep[rep_off[r] + k];
+                p.cigar_off = (int32_t)at;
+                if (p.cigar_len > 0 && k < nc && text_ok) {
+                    const CandState &c = E.cs[cand_off[r] + k];
+                    write_cigar_text(E.cig + c.cig_off, c.cig_n, text + at);
+                }
+                at += p.cigar_len;
             }
-            at += p.cigar_len;
-        }
-        if (junc_off[r + 1] > junc_off[r]) {
-            ReadOut ro; ro.mapq = o.mapq; ro.score = o.score; ro.sub_score = o.sub_score; ro.mis_num = o.mis_num; ro.best = o.best; ro.n_reports = o.n_reports;
-            emit_junctions(E, ro, E.cs + cand_off[r], nc, r, junc + junc_off[r]);
+            if (junc_ok && junc_need > 0) jat += emit_junctions(E, ro[m], E.cs + cand_off[r], nc, r, junc + jat);
         }
     }
 }
@@ -293,8 +291,8 @@ __global__ void k_write_records(Env E, int n_reads, const int64_t *cand_off, con
 
 // buffers owned by the device pipeline (kept across calls inside the context)
 struct DevicePipe {
-    DevBuf<int64_t> cand_off, sv_off, rep_off, text_off, junc_off, cig_off;
-    DevBuf<uint32_t> u32_a, u32_b, text_len, njunc;
+    DevBuf<int64_t> cand_off, sv_off, rep_off;
+    DevBuf<uint32_t> u32_a, u32_b;
     DevBuf<CandState> cs;
     DevBuf<RSeed> pool;
     DevBuf<uint32_t> queue;                  // candidates waiting for phases B, C, D
@@ -441,17 +439,11 @@ void enqueue_pipeline(dartgpu_ctx *c)
     DG_CUDA(cudaGetLastError());
 
     // ---- per read / pair: best, mate rescue, flags, MAPQ; record layout (prefix sums over the reads) ----
-    D->rr.reserve(n + 1); D->rep.reserve(cap_r + 1); D->text_len.reserve(n + 2); D->njunc.reserve(n + 2);
-    D->text_off.reserve(n + 2); D->junc_off.reserve(n + 2);
-    k_read_final<<<grid_for(units), TPB, 0, st>>>(E, units, paired, D->cand_off.p, D->rep_off.p, D->rr.p, D->rep.p, D->text_len.p, D->njunc.p, n);
+    D->rr.reserve(n + 1); D->rep.reserve(cap_r + 1); D->text.reserve(K.text + 1); D->junc.reserve(K.junc + 1);
+    k_read_final<<<grid_for(units), TPB, 0, st>>>(E, units, paired, D->cand_off.p, D->rep_off.p, D->rr.p, D->rep.p, D->text.p, D->junc.p,
+                                                  std::min<int64_t>(K.text, (1ll << 31) - 1), K.junc);
     DG_CUDA(cudaGetLastError());
-    scan_u32(c, D, D->text_len.p, D->text_off.p, n);
-    scan_u32(c, D, D->njunc.p, D->junc_off.p, n);
-    k_ctl_records<<<1, 1, 0, st>>>(ctl, D->text_off.p, D->junc_off.p, n, std::min<int64_t>(K.text, (1ll << 31) - 1), K.junc);
-    D->text.reserve(K.text + 1); D->junc.reserve(K.junc + 1);
-    k_write_records<<<grid_for(n), TPB, 0, st>>>(E, n, D->cand_off.p, D->rr.p, D->rep.p, D->text_off.p, D->text.p, D->junc_off.p, D->junc.p);
-    DG_CUDA(cudaGetLastError());
-    c->stats.kernel_launches += 10;
+    c->stats.kernel_launches += 4;
     auto predict = [&](int64_t last, int64_t cap, int64_t first_guess) {
         int64_t want = last < 0 ? first_guess : (int64_t)((double)last * (double)n / std::max(1, D->last_n) * 1.02) + 4096;
         return std::max<int64_t>(0, std::min(want, cap));

@@ -191,6 +191,9 @@ typedef struct {            /* one UpdateLocalSJMap increment (src/Mapping.cpp:5
     int32_t read;           /* read index in the batch */
 } dartgpu_junction;
 
+/* reads[] and reports[] are in input order.  The slices of cigars[] and junctions[] are laid out in the order the GPU's warps
+ * finished (every report carries its cigar_off, every junction record its read): contents are deterministic, pool layouts
+ * are not. */
 typedef struct {
     const dartgpu_read_result *reads;   int32_t n_reads;
     const dartgpu_report      *reports; int64_t n_reports;
