@@ -106,6 +106,9 @@ __global__ void k_pair_prune(int n_units, int paired, const int64_t *seed_off, c
 // Measured and dropped (round 2, config[1]): running D in the same thread right behind C for the candidates that queued no
 // alignment.  The merged kernel inherits C's 96 registers / 5 CTAs per SM, and these passes are chains of dependent loads
 // whose only remedy is occupancy: phase A-C grew from 0.60 to 1.61 ms while the D pass only shrank from 0.52 to 0.06 ms.
+// Also measured and dropped: two-ended queues that group light candidates (a single seed; nothing but simple pairs) and heavy
+// ones into different warps, with the pool slices and queue places claimed inside k_pair_prune: phase A 0.59 -> 0.62 ms (the
+// queue makes its accesses to the candidate table non-contiguous), phase D 0.60 -> 0.58 ms, k_pair_prune 0.30 -> 0.33 ms.
 // Also measured and dropped: building small CIGARs in a shared-memory buffer instead of the candidate's pool slice (the pairs
 // are written, re-read, reversed and merged in place): 12 KB more shared memory per CTA and generic-address accesses made the
 // D pass 1.9x slower (0.59 -> 1.10 ms).
