@@ -3,11 +3,17 @@
 ("same genome [4.6 Mbp synthetic], 1M paired-end 2x101 bp reads, SAM output, 1 B200").
 
 One step = one pass of the whole hot path (seeds, candidates, 8-mer re-seeding, NW gap fill, pairing, reports)
-over one batch of 1 M synthetic pairs (2 M reads) per GPU.
-  value  reads/s with the read batch already resident in HBM when the timed region starts
-         (dartgpu_map_reads_resident), whole job over all ranks
-  e2e    the same through the public C-ABI call with HOST buffers (dartgpu_map_reads): read H2D and
-         result D2H inside the timed region
+over one batch of 1 M synthetic pairs (2 M reads) per GPU.  ONE host thread per GPU drives CONTEXTS contexts through
+dartgpu_submit / dartgpu_wait (PARTS batches per step) and sleeps while it waits.
+  value   reads/s with the reads AND the result records resident in HBM (no PCIe in the timed region), whole job over all ranks
+          (`value_with_result_copy`: the records copied to page-locked host memory every step — round 1's definition)
+  e2e     the same through the public C-ABI with page-locked HOST buffers: read H2D and result D2H inside the timed region
+  roofline        k_search on this config: L2-bound (index is L2-resident) against the L2 gather peak measured in this run
+  human_scale /   BASELINE config[2] at FULL size (3.1 Gbp genome, spliced pairs) in the same run: value, e2e and the
+  roofline_hbm    HBM-bound roofline of k_search against MEASURED_PEAKS.json
+  cpu_baseline    the stock reference binary on the box's cores; cpu_baseline_hotpath: its per-read functions only (no parse / format / IO)
+  fastq_to_sam    the tool: dart_b200_map vs dart_ref on the same FASTQ files
+  host_link       what the host side of PCIe gives all ranks at once
 Ranks shard reads (each GPU maps its own contiguous 1 M-pair range, index replicated in every HBM): no collective
 on the data path; torch.distributed only provides the barrier and the max-over-ranks of the timing.
 
