@@ -50,7 +50,7 @@ typedef struct {
     int32_t  pair_end;      /* bPairEnd: reads 2i,2i+1 are mates                      */
     int32_t  all_sj;        /* bFindAllJunction (-all_sj)                             */
     int32_t  unique;        /* bUnique (-unique)                                      */
-    int32_t  host_threads;  /* worker threads for the host-side orchestration; 0 = all cores */
+    int32_t  host_threads;  /* OpenMP threads that stage PAGEABLE caller buffers into pinned memory; 0 = all cores */
 } dartgpu_params;
 
 void dartgpu_default_params(dartgpu_params *p);
