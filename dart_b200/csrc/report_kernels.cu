@@ -131,13 +131,18 @@ __device__ __forceinline__ long long warp_claim(long long *counter, int need)
 // active, 26 % of the warp slots occupied).
 struct PhaseQueues { uint32_t *q[3]; };          // candidates waiting for phase 1 (B), 2 (C), 3 (D)
 
-// Occupancy: C keeps the most state live (96 registers), and any kernel that may run it takes its configuration (5 CTAs per
-// SM, 8 staged seeds); D alone runs 6 CTAs per SM (80 registers: with the in-place alignment of tiny blocks 8 CTAs spill; measured
+// Occupancy: C keeps the most state live (96 registers when unconstrained).  Round 1 ran every kernel that may run C at 5 CTAs
+// per SM with 8 staged seeds (64 registers spill and halve the speed); 6 CTAs per SM = 80 registers with 6 staged seeds spills
+// 12-32 bytes and is faster where it matters (config[1], 2 M reads: phase A 0.59 -> 0.46 ms, B 0.07 -> 0.10 ms); D alone runs 6 CTAs per SM (80 registers: with the in-place alignment of tiny blocks 8 CTAs spill; measured
 // 0.68 ms at 8, 0.59 ms at 7 and 6 on config[1]).
 #ifndef PHASE3_CTAS
 #define PHASE3_CTAS 6
 #endif
-template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 3 ? 5 : 8, MIN_CTAS = WHICH == 3 ? PHASE3_CTAS : 5; };
+#ifndef PHASE012_CTAS
+#define PHASE012_CTAS 6
+#define PHASE012_STAGE 6
+#endif
+template <int WHICH> struct PhaseCfg { static constexpr int STAGE = WHICH == 3 ? 5 : PHASE012_STAGE, MIN_CTAS = WHICH == 3 ? PHASE3_CTAS : PHASE012_CTAS; };
 template <int WHICH>
 __global__ void __launch_bounds__(TPB, PhaseCfg<WHICH>::MIN_CTAS) k_phase(Env E, const int64_t *__restrict__ slice_off, long long cap_cig, PhaseQueues Q)
 {
